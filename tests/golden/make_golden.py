@@ -1,0 +1,243 @@
+"""Generate the golden vectors under tests/golden/ by RUNNING THE UNMODIFIED REFERENCE.
+
+Build-container only: imports /root/reference/superpoint (read-only) with oracle/kornia_shim.py standing in
+for the missing kornia package.  The GPU box has no /root/reference; tests read the
+committed .npz files only.
+
+    python tests/golden/make_golden.py
+
+Everything is seeded; weights come from oracle.spn_oracle.make_state_dict (numpy RNG) so the tests can rebuild
+the identical state dict without torch's init RNG.
+"""
+from __future__ import annotations
+
+import copy
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+REF = Path("/root/reference/superpoint")
+OUT = Path(__file__).resolve().parent
+
+from oracle import kornia_shim  # noqa: E402
+from oracle import spn_oracle as O  # noqa: E402
+
+MP_MODEL = {"script": "SuperPoint", "class_name": "SuperPoint", "model_name": "magicpoint",
+            "vgg_cn": [64, 64, 64, 64, 128, 128, 128, 128],
+            "detector_head": {"detector_dim": [128, 256], "grid_size": 8, "nms": 4, "det_thresh": 0.015, "top_k": 0}}
+SP_MODEL = {"script": "SuperPoint", "class_name": "SuperPoint", "model_name": "superpoint",
+            "vgg_cn": [64, 64, 64, 64, 128, 128, 128, 128],
+            "detector_head": {"detector_dim": [128, 256], "grid_size": 8, "nms": 4, "det_thresh": 0.001, "top_k": 50},
+            "descriptor_head": {"descriptor_dim": [128, 256], "grid_size": 8}}
+HA_CFG = {"num": 8, "aggregation": "sum", "filter_counts": 0, "valid_border_margin": 3,
+          "params": {"translation": True, "rotation": True, "scaling": True, "perspective": True,
+                     "scaling_amplitude": 0.2, "perspective_amplitude_x": 0.2, "perspective_amplitude_y": 0.2,
+                     "allow_artifacts": True, "patch_ratio": 0.85, "max_angle": 1.57}}
+
+
+def smooth_image(h, w, seed):
+    """Blurred-noise 'COCO-shaped' test image in [0,1] (numpy only, deterministic)."""
+    rng = np.random.RandomState(seed)
+    img = rng.rand(h, w).astype(np.float32)
+    k = np.array([1, 4, 6, 4, 1], np.float32) / 16
+    for _ in range(2):
+        img = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 1, img)
+        img = np.apply_along_axis(lambda r: np.convolve(r, k, mode="same"), 0, img)
+    img = (img - img.min()) / (img.max() - img.min())
+    return img.astype(np.float32)
+
+
+def main():
+    exper = tempfile.mkdtemp(prefix="spn_golden_")
+    kornia_shim.install(exper_path=exper)
+    sys.path.insert(0, str(REF))
+    from superpoint.models.SuperPoint import SuperPoint
+    from superpoint.models.model_utils.sp_utils import box_nms
+    from superpoint.data.data_utils.homographic_augmentation import Homographic_aug
+    import superpoint.engine_solvers.export as refexport
+
+    torch.set_grad_enabled(False)
+
+    # ---- 1. box_nms known answers -------------------------------------------------------------
+    rng = np.random.RandomState(1)
+    cases = {}
+    ci = 0
+    for (h, w, size, min_prob, topk, kind) in [
+        (48, 64, 4, 0.015, 0, "dense"), (48, 64, 4, 0.001, 20, "dense"), (40, 56, 3, 0.3, 0, "uniform"),
+        (40, 56, 8, 0.0, 0, "uniform"), (32, 48, 4, 0.1, 0, "ties"), (32, 48, 4, 0.1, 7, "ramp"),
+        (24, 24, 4, 0.5, 0, "tie3"), (16, 16, 4, 2.0, 0, "empty"), (64, 80, 2, 0.2, 0, "uniform"),
+        (30, 40, 5, 0.2, 11, "uniform"),
+    ]:
+        if kind == "dense":
+            p = (1 / 65 + 0.001 * rng.randn(h, w)).astype(np.float32)
+        elif kind == "uniform":
+            p = rng.rand(h, w).astype(np.float32)
+        elif kind == "ties":
+            p = (np.round(rng.rand(h, w) * 8) / 8).astype(np.float32)
+        elif kind == "ramp":
+            p = (np.arange(h * w, dtype=np.float32).reshape(h, w)[::-1, ::-1] / (h * w)).copy()
+        elif kind == "tie3":
+            p = np.zeros((h, w), np.float32)
+            p[5, 5] = p[5, 6] = p[6, 5] = 0.5
+            p[20, 3] = 0.9
+        else:
+            p = rng.rand(h, w).astype(np.float32)
+        out = box_nms(torch.from_numpy(p), size, min_prob=min_prob, keep_top_k=topk).numpy()
+        cases[f"c{ci}_prob"] = p
+        cases[f"c{ci}_out"] = out
+        cases[f"c{ci}_par"] = np.array([size, 0.1, min_prob, topk], np.float64)
+        ci += 1
+    cases["n"] = np.array(ci)
+    np.savez_compressed(OUT / "nms_cases.npz", **cases)
+
+    # ---- 2. model forward ---------------------------------------------------------------------
+    for tag, mcfg, seed, gain, shape in [("magicpoint", MP_MODEL, 3, 12.0, (2, 1, 48, 64)),
+                                         ("superpoint", SP_MODEL, 4, 12.0, (1, 1, 40, 48))]:
+        sd = O.make_state_dict(mcfg["model_name"], seed=seed, logit_gain=gain)
+        model = SuperPoint(copy.deepcopy(mcfg)).eval()
+        model.load_state_dict(sd)
+        x = torch.from_numpy(np.stack([smooth_image(shape[2], shape[3], 10 + i) for i in range(shape[0])])[:, None])
+        out = model(x)
+        d = {"x": x.numpy(), "seed": np.array(seed), "gain": np.array(gain),
+             "logits": out["detector_output"]["logits"].numpy(),
+             "prob_heatmap": out["detector_output"]["prob_heatmap"].numpy(),
+             "prob_heatmap_nms": out["detector_output"]["prob_heatmap_nms"].numpy(),
+             "pred_pts": out["detector_output"]["pred_pts"].numpy()}
+        if "descriptor_output" in out:
+            d["desc_raw"] = out["descriptor_output"]["desc_raw"].numpy()
+            desc = out["descriptor_output"]["desc"].numpy()
+            pr = np.random.RandomState(5)
+            ys = pr.randint(0, shape[2], 64)
+            xs = pr.randint(0, shape[3], 64)
+            ys[:4] = [0, 0, shape[2] - 1, shape[2] - 1]
+            xs[:4] = [0, shape[3] - 1, 0, shape[3] - 1]
+            d["desc_pts"] = np.stack([ys, xs], 1).astype(np.int64)
+            d["desc_at_pts"] = desc[0][:, ys, xs].T.copy()  # (64,256)
+            d["desc_shape"] = np.array(desc.shape)
+        np.savez_compressed(OUT / f"forward_{tag}.npz", **d)
+
+    # ---- 3. homography sampler ----------------------------------------------------------------
+    aug = Homographic_aug({"params": HA_CFG["params"], "valid_border_margin": 3}, "cpu")
+    hs = {}
+    for seed in range(6):
+        np.random.seed(seed)
+        hs[f"s{seed}"] = torch.cat([aug.sample_homography((240, 320), **HA_CFG["params"]) for _ in range(3)]).numpy()
+    np.random.seed(100)
+    p2 = dict(HA_CFG["params"], allow_artifacts=False, patch_ratio=0.5, n_scales=5, n_angles=25, translation_overflow=0.0)
+    hs["noartifact"] = torch.cat([aug.sample_homography((120, 160), **p2) for _ in range(3)]).numpy()
+    np.savez_compressed(OUT / "homographies.npz", **hs)
+
+    # ---- 4. one ExportDetections.step: warped image / mask / count / projection -----------------
+    img = torch.from_numpy(smooth_image(120, 160, 21))[None, None]
+    np.random.seed(7)
+    Hs = torch.cat([aug.sample_homography((120, 160), **HA_CFG["params"]) for _ in range(3)])
+    steps = {"image": img.numpy(), "H": Hs.numpy()}
+
+    class FakeModel:
+        def __init__(self):
+            self.seen = []
+
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            self.seen.append(x.clone())
+            # a smooth, position-dependent "probability" so the projection is informative
+            return {"detector_output": {"prob_heatmap": (0.25 + 0.5 * x[:, 0]).clone()}}
+
+    exp = object.__new__(refexport.ExportDetections)
+    exp.config = {"homography_adaptation": HA_CFG}
+    exp.device = "cpu"
+    exp.model = FakeModel()
+    for i in range(3):
+        class One:
+            def sample_homography(self, shape, **kw):
+                return Hs[i:i + 1]
+        exp.one_homography = One()
+        probs0 = torch.zeros((1, 1, 120, 160))
+        counts0 = torch.ones((1, 1, 120, 160))
+        probs, counts = exp.step(img, probs0, counts0)
+        steps[f"warped{i}"] = exp.model.seen[-1][0, 0].numpy()
+        steps[f"proj{i}"] = probs[0, 1].numpy()
+        steps[f"count{i}"] = counts[0, 1].numpy().astype(np.int32)
+        # mask = erosion(nearest warp of ones by H): recover it through a second call whose "model" returns ones
+        m = refexport.kornia.morphology.erosion(
+            refexport.K.warp_perspective(torch.ones_like(img), Hs[i:i + 1], dsize=(120, 160), mode="nearest", align_corners=True),
+            O.erosion_kernel(3))
+        steps[f"mask{i}"] = m[0, 0].numpy().astype(np.int32)
+    np.savez_compressed(OUT / "ha_step.npz", **steps)
+
+    # ---- 5. end-to-end ExportDetections (HA, 8 homographies, 120x160) ---------------------------
+    sd = O.make_state_dict("magicpoint", seed=11, logit_gain=12.0)
+    model = SuperPoint(copy.deepcopy(MP_MODEL)).eval()
+    model.load_state_dict(sd)
+    config = {"data": {"experiment_name": "golden"}, "homography_adaptation": HA_CFG, "model": copy.deepcopy(MP_MODEL)}
+    img = torch.from_numpy(smooth_image(120, 160, 33))[None, None]
+    captured = {}
+    orig_nms = refexport.box_nms
+
+    def spy_nms(prob, **kw):
+        captured["agg"] = prob.clone()
+        r = orig_nms(prob=prob, **kw)
+        captured["nms"] = r.clone()
+        return r
+
+    used_h = []
+    orig_sample = Homographic_aug.sample_homography
+
+    def spy_sample(self, *a, **kw):
+        h = orig_sample(self, *a, **kw)
+        used_h.append(h.clone())
+        return h
+
+    refexport.box_nms = spy_nms
+    Homographic_aug.sample_homography = spy_sample
+    np.random.seed(123)
+    refexport.ExportDetections(config, model, [{"raw": {"image": img}, "name": ["img0"]}], "training", True, "cpu")
+    refexport.box_nms = orig_nms
+    Homographic_aug.sample_homography = orig_sample
+    kp = np.load(Path(exper, "outputs", "golden", "training", "img0.npy"))
+    np.savez_compressed(OUT / "ha_export.npz", image=img.numpy(), H=torch.cat(used_h).numpy(), agg=captured["agg"].numpy(),
+                        nms=captured["nms"].numpy(), keypoints=kp, seed=np.array(11), gain=np.array(12.0), np_seed=np.array(123))
+    print("ha_export keypoints", kp.shape, kp.dtype)
+
+    # ---- 6. HPatches-style exports: file layout --------------------------------------------------
+    sdp = O.make_state_dict("superpoint", seed=4, logit_gain=12.0)
+    model = SuperPoint(copy.deepcopy(SP_MODEL)).eval()
+    model.load_state_dict(sdp)
+    im1 = torch.from_numpy(smooth_image(40, 48, 50))[None, None]
+    np.random.seed(9)
+    Hgt = aug.sample_homography((40, 48), **HA_CFG["params"])
+    im2 = kornia_shim.warp_perspective(im1, Hgt, (40, 48))
+    loader = [{"image": im1, "warped_image": im2, "homography": Hgt, "name": ["pair0"]}]
+    cfg = {"data": {"experiment_name": "golden_hp"}, "model": copy.deepcopy(SP_MODEL)}
+    refexport.Export_Hpatches_Repeatability(cfg, model, loader, "cpu")
+    refexport.Export_Hpatches_Descriptors(cfg, model, loader, "cpu")
+    rep = np.load(Path(exper, "repeatability", "golden_hp", "pair0.npz"))
+    des = np.load(Path(exper, "descriptors", "golden_hp", "pair0.npz"))
+    layout = {"image": im1.numpy(), "warped_image": im2.numpy(), "homography": Hgt.numpy()}
+    for k in rep.files:
+        layout[f"rep__{k}__shape"] = np.array(rep[k].shape)
+        layout[f"rep__{k}__dtype"] = np.array(str(rep[k].dtype))
+    for k in des.files:
+        layout[f"des__{k}__shape"] = np.array(des[k].shape)
+        layout[f"des__{k}__dtype"] = np.array(str(des[k].dtype))
+    layout["rep_prob"] = rep["prob"]
+    layout["rep_warped_prob"] = rep["warped_prob"]
+    pr = np.random.RandomState(6)
+    ys, xs = pr.randint(0, 40, 32), pr.randint(0, 48, 32)
+    layout["des_pts"] = np.stack([ys, xs], 1)
+    layout["des_desc_at_pts"] = des["desc"][ys, xs]          # (32,256) from the (H,W,256) layout
+    layout["des_warped_desc_at_pts"] = des["warped_desc"][ys, xs]
+    np.savez_compressed(OUT / "hpatches_export.npz", **layout)
+    for f in sorted(OUT.glob("*.npz")):
+        print(f.name, f.stat().st_size)
+
+
+if __name__ == "__main__":
+    main()
