@@ -1,0 +1,142 @@
+/* spn_b200.h - C ABI of the B200-native SuperPoint/MagicPoint inference hot path.
+ *
+ * The reference (AliYoussef97/SuperPoint-NeRF-Pytorch) is pure Python; the functions below are what a
+ * ctypes/cffi binding inside the reference would call in place of the PyTorch/kornia/torchvision calls
+ * cited next to each entry point (paths relative to superpoint/superpoint/ in the reference).
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; h_* is a HOST pointer;
+ *   - shapes are explicit ints, tensors are dense row-major in the order written in the comment;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no implicit synchronisation
+ *     except when the context's internal workspace has to grow (first call with a bigger shape);
+ *   - return 0 on success, a negative SPN_E_* code on failure; spn_last_error() gives the message
+ *     (thread-local); no C++ exception crosses the boundary;
+ *   - CUDA only, sm_100a only: there is no CPU fallback.
+ */
+#ifndef SPN_B200_H
+#define SPN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SPN_API __attribute__((visibility("default")))
+#else
+#define SPN_API
+#endif
+
+typedef struct spn_ctx spn_ctx;
+typedef void* spn_stream; /* cudaStream_t */
+
+enum {
+  SPN_OK = 0,
+  SPN_E_INVALID = -1, /* bad argument / unsupported shape */
+  SPN_E_CUDA = -2,    /* CUDA runtime error */
+  SPN_E_STATE = -3,   /* weights missing, encoder not run, ... */
+  SPN_E_NOMEM = -4
+};
+
+/* layer ids, in the order of the reference's state-dict prefixes
+ * (models/model_utils/VGG_Backbone.py:44-58, models/model_utils/heads.py:11-13,54-56) */
+enum {
+  SPN_L_BLOCK1 = 0, SPN_L_BLOCK2, SPN_L_BLOCK3, SPN_L_BLOCK4, SPN_L_BLOCK5, SPN_L_BLOCK6, SPN_L_BLOCK7, SPN_L_BLOCK8,
+  SPN_L_CONVPA = 8, SPN_L_CONVPB = 9, SPN_L_CONVDA = 10, SPN_L_CONVDB = 11, SPN_NUM_LAYERS = 12
+};
+
+/* numeric mode of the convolutions */
+enum {
+  SPN_MODE_FP32 = 0, /* strict: fp32 FFMA convolutions (1e-4 parity gate)                       */
+  SPN_MODE_F16 = 1,  /* fast: tcgen05 implicit GEMM, fp16 operands, fp32 accumulate (5e-3 gate) */
+  SPN_MODE_BF16 = 2  /* fast: tcgen05 implicit GEMM, bf16 operands, fp32 accumulate             */
+};
+
+SPN_API const char* spn_last_error(void);
+SPN_API int spn_version(void);
+
+/* Context: device weights, workspace, TMA descriptors.  One per (process, GPU). */
+SPN_API int spn_create(spn_ctx** out, int device);
+SPN_API int spn_destroy(spn_ctx* ctx);
+
+/* BN fold + pack + upload of one VGG_Block (conv2d + BatchNorm2d eval, eps as given).
+ * Replaces nn.Conv2d/nn.BatchNorm2d parameter storage (VGG_Backbone.py:11-14) as loaded by engine.py:108-117.
+ * h_w [cout][cin][k][k], h_b/h_gamma/h_beta/h_mean/h_var [cout] are HOST fp32 arrays. */
+SPN_API int spn_pack_weights(spn_ctx* ctx, int layer, const float* h_w, const float* h_b, const float* h_gamma,
+                     const float* h_beta, const float* h_mean, const float* h_var, float eps, int cout, int cin,
+                     int ksize, spn_stream stream);
+
+/* VGG_BACKBONE.forward (VGG_Backbone.py:60-71): d_images [B][H][W] fp32 in [0,1] -> feature map kept inside ctx
+ * (H, W multiples of 8). */
+SPN_API int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode, spn_stream stream);
+
+/* Detector_head.forward up to prob_heatmap (heads.py:17-28): convPa, convPb, softmax(65), drop dustbin,
+ * pixel_shuffle(8).  d_mask (nullable) [B][H][W] u8 multiplies the heatmap (export.py:70).
+ * d_logits (nullable) [B][65][H/8][W/8]; d_prob [B][H][W]. */
+SPN_API int spn_detector_head_forward(spn_ctx* ctx, int B, int H, int W, int mode, const uint8_t* d_mask, float* d_logits,
+                              float* d_prob, spn_stream stream);
+
+/* Descriptor_head.forward up to desc_raw (heads.py:61-63): convDa, convDb.  d_desc_raw [B][256][H/8][W/8]. */
+SPN_API int spn_descriptor_head_forward(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw, spn_stream stream);
+
+/* F.interpolate(bicubic, x grid, align_corners=False) + F.normalize(p=2, dim=1) (heads.py:65-66), dense.
+ * d_desc_raw [B][C][Hc][Wc] -> d_desc [B][C][Hc*grid][Wc*grid]. */
+SPN_API int spn_dense_descriptors(spn_ctx* ctx, const float* d_desc_raw, int B, int C, int Hc, int Wc, int grid, float* d_desc,
+                          spn_stream stream);
+
+/* The same value as dense desc[:, :, y, x] evaluated only at keypoints (what the consumers index:
+ * evaluations/descriptor_evaluation.py:67-69).  d_kp [B][max_kp][2] int32 (row, col), d_kp_count [B];
+ * d_out [B][max_kp][C].  interp: 0 = bicubic (reference parity), 1 = bilinear. */
+SPN_API int spn_sample_descriptors(spn_ctx* ctx, const float* d_desc_raw, int B, int C, int Hc, int Wc, int grid,
+                           const int32_t* d_kp, const int32_t* d_kp_count, int max_kp, int interp, float* d_out,
+                           spn_stream stream);
+
+/* box_nms (sp_utils.py:4-28) + threshold (heads.py:41 / export.py:123) + nonzero (export.py:125), batched.
+ * d_prob [B][H][W]; outputs (each nullable): d_nms [B][H][W] fp32, d_pred [B][H][W] int32 (= nms >= det_thresh),
+ * d_kp [B][max_kp][2] int32 (row, col) in row-major order, d_kp_count [B] (true count, may exceed max_kp). */
+SPN_API int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H, int W, float size, float iou, float min_prob,
+                     int top_k, float det_thresh, float* d_nms, int32_t* d_pred, int32_t* d_kp, int32_t* d_kp_count,
+                     int max_kp, spn_stream stream);
+
+/* ExportDetections.step warp part (export.py:51-66): for every image i < n_images and homography j < n_h
+ *   slot = i*(n_h+1) + 1 + j : d_warped[slot] = warp_perspective(image_i, H_ij, bilinear, align_corners=True)
+ *                              d_mask[slot]   = erosion(warp_perspective(ones, H_ij, nearest), ellipse(2*margin))
+ *   slot = i*(n_h+1)         : the image itself, mask = 1 (identity forward, export.py:93)
+ * d_hinv [n_images][n_h][9] fp32 are the pixel-space INVERSES of the matrices the reference passes
+ * (kornia samples src at M^-1 p).  d_images [n_images][H][W]; d_warped [n_images*(n_h+1)][H][W] fp32;
+ * d_mask same shape u8. */
+SPN_API int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H, int W,
+                   int margin, float* d_warped, uint8_t* d_mask, spn_stream stream);
+
+/* ExportDetections.step projection + homography_adaptation aggregation (export.py:72-77,106-114):
+ * for every image: out(p) = [ prob_0(p) + sum_j count_j(p) * bilinear(prob_j, H_j p) ] / [ 1 + sum_j count_j(p) ]
+ * with count_j = erosion(nearest warp of ones by H_j^-1)  (aggregation 0 = 'sum'), or the max over the same
+ * terms (aggregation 1 = 'max').  d_probs [n_images][n_h+1][H][W] (already multiplied by the masks),
+ * d_h [n_images][n_h][9] fp32 pixel-space H as the reference samples them; d_out [n_images][H][W]. */
+SPN_API int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float* d_h, int n_images, int n_h, int H, int W,
+                     int margin, int aggregation, float* d_out, spn_stream stream);
+
+/* Homographic_aug.sample_homography (data/data_utils/homographic_augmentation.py:21-106) on the device:
+ * counter-based RNG keyed by (seed, first_index + i); truncated normals, scale/angle choice, translation,
+ * 4-point DLT solve in fp64, fp32 inverse.  Writes d_h [count][9] (what the reference returns) and
+ * d_hinv [count][9].  Statistically equivalent to, not bit-equal with, the numpy-RNG reference. */
+typedef struct spn_homography_params {
+  int translation, rotation, scaling, perspective;
+  float scaling_amplitude, perspective_amplitude_x, perspective_amplitude_y, patch_ratio, max_angle,
+      translation_overflow;
+  int n_scales, n_angles, allow_artifacts;
+} spn_homography_params;
+SPN_API int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params* params, uint64_t seed, uint64_t first_index,
+                            int count, int H, int W, float* d_h, float* d_hinv, spn_stream stream);
+
+/* 3x3 inverse, fp32, batched (export.py:49 torch.inverse). d_in/d_out [count][9]. */
+SPN_API int spn_invert3x3(spn_ctx* ctx, const float* d_in, int count, float* d_out, spn_stream stream);
+
+/* number of kernels launched through this context since creation (bench.py's gpu_launches) */
+SPN_API int64_t spn_launch_count(spn_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPN_B200_H */

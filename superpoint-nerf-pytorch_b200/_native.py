@@ -1,0 +1,262 @@
+"""ctypes binding of include/spn_b200.h.  PyTorch is used only for device memory and streams."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libspn_b200.so"
+
+MODE_FP32, MODE_F16, MODE_BF16 = 0, 1, 2
+MODES = {"fp32": MODE_FP32, "f16": MODE_F16, "fp16": MODE_F16, "bf16": MODE_BF16}
+
+LAYER_PREFIXES = [
+    "backbone.block_1", "backbone.block_2", "backbone.block_3", "backbone.block_4",
+    "backbone.block_5", "backbone.block_6", "backbone.block_7", "backbone.block_8",
+    "detector_head.convPa", "detector_head.convPb", "descriptor_head.convDa", "descriptor_head.convDb",
+]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class HomographyParams(C.Structure):
+    _fields_ = [("translation", C.c_int), ("rotation", C.c_int), ("scaling", C.c_int), ("perspective", C.c_int),
+                ("scaling_amplitude", C.c_float), ("perspective_amplitude_x", C.c_float),
+                ("perspective_amplitude_y", C.c_float), ("patch_ratio", C.c_float), ("max_angle", C.c_float),
+                ("translation_overflow", C.c_float), ("n_scales", C.c_int), ("n_angles", C.c_int),
+                ("allow_artifacts", C.c_int)]
+
+
+_vp, _i, _f = C.c_void_p, C.c_int, C.c_float
+# name -> (restype, argtypes); must list every symbol include/spn_b200.h declares
+PROTOTYPES = {
+    "spn_last_error": (C.c_char_p, []),
+    "spn_version": (_i, []),
+    "spn_create": (_i, [C.POINTER(_vp), _i]),
+    "spn_destroy": (_i, [_vp]),
+    "spn_pack_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "spn_encoder_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "spn_detector_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "spn_descriptor_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "spn_dense_descriptors": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "spn_sample_descriptors": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "spn_box_nms_topk": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "spn_warp_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "spn_ha_aggregate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "spn_sample_homographies": (_i, [_vp, C.POINTER(HomographyParams), C.c_uint64, C.c_uint64, _i, _i, _i, _vp, _vp, _vp]),
+    "spn_invert3x3": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "spn_launch_count": (C.c_int64, [_vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def library_path() -> Path:
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libspn_b200.so and bind every prototype.  Fails loudly (no fallback) if it is missing."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not _LIB_PATH.exists():
+                raise NativeError(f"{_LIB_PATH} not found: build it with `python superpoint-nerf-pytorch_b200/build.py` "
+                                  "(there is no CPU/PyTorch fallback)")
+            lib = C.CDLL(str(_LIB_PATH))
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk_dev(t: torch.Tensor, dtype, name):
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise NativeError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise NativeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise NativeError(f"{name} must be contiguous")
+
+
+class Context:
+    """Owns one spn_ctx (device weights + workspace) on one GPU."""
+
+    def __init__(self, device: int | None = None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise NativeError("CUDA is not available: superpoint-nerf-pytorch_b200 has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        h = C.c_void_p()
+        self._call("spn_create", C.byref(h), self.device)
+        self.handle = h
+        self._weights_key = None
+
+    def _call(self, name, *args):
+        rc = getattr(self.lib, name)(*args)
+        if rc != 0:
+            raise NativeError(f"{name} failed ({rc}): {self.lib.spn_last_error().decode(errors='replace')}")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.spn_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.spn_launch_count(self.handle))
+
+    # ---- weights -------------------------------------------------------------------------------
+    def load_state_dict(self, sd: dict, eps: float = 1e-5):
+        """Fold BN and upload every VGG_Block present in a reference-format state dict (engine.py:108-117)."""
+        for lid, pre in enumerate(LAYER_PREFIXES):
+            if f"{pre}.conv2d.weight" not in sd:
+                continue
+            get = lambda k: sd[f"{pre}.{k}"].detach().to("cpu", torch.float32).contiguous()  # noqa: E731
+            w, b = get("conv2d.weight"), get("conv2d.bias")
+            g, be, mu, var = get("norm.weight"), get("norm.bias"), get("norm.running_mean"), get("norm.running_var")
+            cout, cin, k, _ = w.shape
+            self._call("spn_pack_weights", self.handle, lid, _ptr(w), _ptr(b), _ptr(g), _ptr(be), _ptr(mu), _ptr(var),
+                       C.c_float(eps), cout, cin, k, _stream())
+
+    # ---- forward -------------------------------------------------------------------------------
+    def encoder_forward(self, images: torch.Tensor, mode: int):
+        _chk_dev(images, torch.float32, "images")
+        B, H, W = images.shape
+        self._call("spn_encoder_forward", self.handle, _ptr(images), B, H, W, mode, _stream())
+
+    def detector_head_forward(self, B, H, W, mode, mask=None, want_logits=False, out=None):
+        dev = torch.device("cuda", self.device)
+        if out is None:
+            prob = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        else:
+            _chk_dev(out, torch.float32, "out")
+            if tuple(out.shape) != (B, H, W):
+                raise NativeError(f"out must be {(B, H, W)}, got {tuple(out.shape)}")
+            prob = out
+        logits = torch.empty((B, 65, H // 8, W // 8), dtype=torch.float32, device=dev) if want_logits else None
+        if mask is not None:
+            _chk_dev(mask, torch.uint8, "mask")
+        self._call("spn_detector_head_forward", self.handle, B, H, W, mode, _ptr(mask), _ptr(logits), _ptr(prob), _stream())
+        return prob, logits
+
+    def descriptor_head_forward(self, B, H, W, mode):
+        raw = torch.empty((B, 256, H // 8, W // 8), dtype=torch.float32, device=torch.device("cuda", self.device))
+        self._call("spn_descriptor_head_forward", self.handle, B, H, W, mode, _ptr(raw), _stream())
+        return raw
+
+    def dense_descriptors(self, raw: torch.Tensor, grid: int):
+        _chk_dev(raw, torch.float32, "desc_raw")
+        B, Cc, Hc, Wc = raw.shape
+        out = torch.empty((B, Cc, Hc * grid, Wc * grid), dtype=torch.float32, device=raw.device)
+        self._call("spn_dense_descriptors", self.handle, _ptr(raw), B, Cc, Hc, Wc, grid, _ptr(out), _stream())
+        return out
+
+    def sample_descriptors(self, raw, grid, kp, kp_count, interp="bicubic"):
+        _chk_dev(raw, torch.float32, "desc_raw")
+        _chk_dev(kp, torch.int32, "kp")
+        _chk_dev(kp_count, torch.int32, "kp_count")
+        B, Cc, Hc, Wc = raw.shape
+        max_kp = kp.shape[1]
+        out = torch.zeros((B, max_kp, Cc), dtype=torch.float32, device=raw.device)
+        self._call("spn_sample_descriptors", self.handle, _ptr(raw), B, Cc, Hc, Wc, grid, _ptr(kp), _ptr(kp_count), max_kp,
+                   0 if interp == "bicubic" else 1, _ptr(out), _stream())
+        return out
+
+    def box_nms(self, prob, size, iou=0.1, min_prob=0.01, top_k=0, det_thresh=None, want_map=True, want_pred=False,
+                max_kp=0):
+        """prob (B,H,W).  Returns dict(nms, pred, kp, kp_count) with the requested members."""
+        _chk_dev(prob, torch.float32, "prob")
+        B, H, W = prob.shape
+        dev = prob.device
+        det = float(min_prob if det_thresh is None else det_thresh)
+        out = {"nms": torch.empty_like(prob) if want_map else None,
+               "pred": torch.empty((B, H, W), dtype=torch.int32, device=dev) if want_pred else None,
+               "kp": torch.zeros((B, max_kp, 2), dtype=torch.int32, device=dev) if max_kp else None,
+               "kp_count": torch.zeros((B,), dtype=torch.int32, device=dev) if max_kp else None}
+        self._call("spn_box_nms_topk", self.handle, _ptr(prob), B, H, W, C.c_float(size), C.c_float(iou), C.c_float(min_prob),
+                   int(top_k), C.c_float(det), _ptr(out["nms"]), _ptr(out["pred"]), _ptr(out["kp"]), _ptr(out["kp_count"]),
+                   int(max_kp), _stream())
+        return out
+
+    # ---- homography adaptation -------------------------------------------------------------------
+    def warp_batch(self, images, hinv, margin):
+        """images (NI,H,W), hinv (NI,n_h,3,3) -> warped (NI*(n_h+1),H,W) fp32, mask u8 (same shape)."""
+        _chk_dev(images, torch.float32, "images")
+        NI, H, W = images.shape
+        n_h = 0 if hinv is None else hinv.shape[1]
+        if n_h:
+            _chk_dev(hinv, torch.float32, "hinv")
+        warped = torch.empty((NI * (n_h + 1), H, W), dtype=torch.float32, device=images.device)
+        mask = torch.empty((NI * (n_h + 1), H, W), dtype=torch.uint8, device=images.device)
+        self._call("spn_warp_batch", self.handle, _ptr(images), NI, _ptr(hinv) if n_h else None, n_h, H, W, int(margin),
+                   _ptr(warped), _ptr(mask), _stream())
+        return warped, mask
+
+    def ha_aggregate(self, probs, h, margin, aggregation="sum"):
+        """probs (NI,n_h+1,H,W) masked heatmaps, h (NI,n_h,3,3) -> (NI,H,W)."""
+        _chk_dev(probs, torch.float32, "probs")
+        NI, n1, H, W = probs.shape
+        n_h = n1 - 1
+        if n_h:
+            _chk_dev(h, torch.float32, "h")
+        out = torch.empty((NI, H, W), dtype=torch.float32, device=probs.device)
+        self._call("spn_ha_aggregate", self.handle, _ptr(probs), _ptr(h) if n_h else None, NI, n_h, H, W, int(margin),
+                   1 if aggregation == "max" else 0, _ptr(out), _stream())
+        return out
+
+    def sample_homographies(self, params: dict, seed: int, first_index: int, count: int, H: int, W: int):
+        p = HomographyParams(
+            int(params.get("translation", True)), int(params.get("rotation", True)), int(params.get("scaling", True)),
+            int(params.get("perspective", True)), float(params.get("scaling_amplitude", 0.1)),
+            float(params.get("perspective_amplitude_x", 0.1)), float(params.get("perspective_amplitude_y", 0.1)),
+            float(params.get("patch_ratio", 0.5)), float(params.get("max_angle", 1.57)),
+            float(params.get("translation_overflow", 0.0)), int(params.get("n_scales", 5)), int(params.get("n_angles", 25)),
+            int(params.get("allow_artifacts", False)))
+        dev = torch.device("cuda", self.device)
+        h = torch.empty((count, 3, 3), dtype=torch.float32, device=dev)
+        hinv = torch.empty((count, 3, 3), dtype=torch.float32, device=dev)
+        self._call("spn_sample_homographies", self.handle, C.byref(p), C.c_uint64(seed), C.c_uint64(first_index), count, H, W,
+                   _ptr(h), _ptr(hinv), _stream())
+        return h, hinv
+
+    def invert3x3(self, m):
+        _chk_dev(m, torch.float32, "m")
+        out = torch.empty_like(m)
+        self._call("spn_invert3x3", self.handle, _ptr(m), m.numel() // 9, _ptr(out), _stream())
+        return out
+
+
+_contexts: dict[int, Context] = {}
+
+
+def get_context(device=None) -> Context:
+    """Process-wide context per GPU (weights are per-model: models create their own Context)."""
+    if not torch.cuda.is_available():
+        raise NativeError("CUDA is not available: superpoint-nerf-pytorch_b200 has no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if idx not in _contexts:
+        _contexts[idx] = Context(idx)
+    return _contexts[idx]

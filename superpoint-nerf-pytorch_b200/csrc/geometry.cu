@@ -1,0 +1,393 @@
+// Homography kernels: batched bilinear warp + eroded validity mask, the fused inverse-warp / count-normalised
+// aggregation over homographies, the device homography sampler and a batched 3x3 inverse.
+//
+// Reference semantics (superpoint/superpoint/engine_solvers/export.py:42-114 and kornia 0.7.0 as restated in
+// oracle/kornia_shim.py): warp_perspective(src, M)(p) = interp(src, M^-1 p), align_corners=True, zeros padding,
+// nearest = round-half-even; erosion = min over the elliptical structuring element
+// cv2.getStructuringElement(MORPH_ELLIPSE, (2m,2m)) with origin (m,m) and a geodesic border (pixels outside the
+// image never erode).
+//
+// Both kernels are HBM/L2-bandwidth bound (a few FLOPs per byte): they are tiled 32x8 pixels per CTA with the
+// raw validity bits of the tile + erosion halo staged in shared memory, coalesced row-major global accesses, and
+// grids of (tiles x slots) CTAs = many multiples of the 148 SMs.
+#include <math.h>
+
+#include "spn_common.cuh"
+
+namespace {
+
+constexpr int kTileW = 32, kTileH = 8, kMaxKs = 16;
+constexpr int kRawH = kTileH + kMaxKs - 1, kRawW = kTileW + kMaxKs;  // 23 x 48
+
+struct ErodeK {
+  int ks;              // structuring element is ks x ks
+  int org;             // origin = ks/2
+  uint32_t rows[kMaxKs];
+};
+
+// cv2.getStructuringElement(MORPH_ELLIPSE, (ks,ks)) restated (export.py:59).
+ErodeK make_ellipse(int margin) {
+  ErodeK e;
+  memset(&e, 0, sizeof(e));
+  const int ks = 2 * margin;
+  e.ks = ks;
+  e.org = ks / 2;
+  const int r = ks / 2, c = ks / 2;
+  const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+  for (int i = 0; i < ks; ++i) {
+    const int dy = i - r;
+    int j1 = 0, j2 = 0;
+    if (abs(dy) <= r) {
+      const int dx = (int)lrint(c * sqrt((r * r - dy * dy) * inv_r2));
+      j1 = max(c - dx, 0);
+      j2 = min(c + dx + 1, ks);
+    }
+    for (int j = j1; j < j2; ++j) e.rows[i] |= 1u << j;
+  }
+  return e;
+}
+
+// src = M p  (p = (x, y, 1)) with kornia's homogeneous divide: scale = |z| > 1e-8 ? 1/(z + 1e-8) : 1
+__device__ __forceinline__ void apply_h(const float* __restrict__ m, float x, float y, float& sx, float& sy) {
+  const float nx = fmaf(m[0], x, fmaf(m[1], y, m[2]));
+  const float ny = fmaf(m[3], x, fmaf(m[4], y, m[5]));
+  const float z = fmaf(m[6], x, fmaf(m[7], y, m[8]));
+  const float sc = fabsf(z) > 1e-8f ? 1.0f / (z + 1e-8f) : 1.0f;
+  sx = nx * sc;
+  sy = ny * sc;
+}
+
+// grid_sample(mode='nearest', padding 'zeros') of an all-ones image: 1 iff the rounded coordinate is inside.
+__device__ __forceinline__ int inside_nearest(float sx, float sy, int H, int W) {
+  const float rx = rintf(sx), ry = rintf(sy);
+  return (rx >= 0.f && rx <= (float)(W - 1) && ry >= 0.f && ry <= (float)(H - 1)) ? 1 : 0;
+}
+
+// grid_sample(mode='bilinear', padding 'zeros', align_corners=True) of one channel.
+__device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, float sx, float sy, int H, int W) {
+  if (!(sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H)) return 0.f;  // also rejects NaN/inf
+  const float fx = floorf(sx), fy = floorf(sy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float wx1 = sx - fx, wy1 = sy - fy;
+  const float wx0 = (fx + 1.f) - sx, wy0 = (fy + 1.f) - sy;
+  const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
+  const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
+  float v = 0.f;
+  if (yin0 && xin0) v = fmaf(__ldg(&img[(size_t)y0 * W + x0]), wx0 * wy0, v);
+  if (yin0 && xin1) v = fmaf(__ldg(&img[(size_t)y0 * W + x0 + 1]), wx1 * wy0, v);
+  if (yin1 && xin0) v = fmaf(__ldg(&img[(size_t)(y0 + 1) * W + x0]), wx0 * wy1, v);
+  if (yin1 && xin1) v = fmaf(__ldg(&img[(size_t)(y0 + 1) * W + x0 + 1]), wx1 * wy1, v);
+  return v;
+}
+
+// Raw (un-eroded) validity of the tile + halo for matrix m; pixels outside the image count as valid (geodesic).
+__device__ __forceinline__ void fill_raw(uint8_t (*raw)[kRawW], const float* m, const ErodeK& ek, int tx0, int ty0,
+                                         int H, int W) {
+  const int rh = kTileH + ek.ks - 1, rw = kTileW + ek.ks - 1;
+  for (int i = threadIdx.x; i < rh * rw; i += blockDim.x) {
+    const int ry = i / rw, rx = i - ry * rw;
+    const int y = ty0 + ry - ek.org, x = tx0 + rx - ek.org;
+    int v = 1;
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+      float sx, sy;
+      apply_h(m, (float)x, (float)y, sx, sy);
+      v = inside_nearest(sx, sy, H, W);
+    }
+    raw[ry][rx] = (uint8_t)v;
+  }
+}
+
+__device__ __forceinline__ int eroded_at(const uint8_t (*raw)[kRawW], const ErodeK& ek, int tx, int ty) {
+  int m = 1;
+  for (int i = 0; i < ek.ks; ++i) {
+    const uint32_t bits = ek.rows[i];
+    for (int j = 0; j < ek.ks; ++j)
+      if ((bits >> j) & 1u) m &= raw[ty + i][tx + j];
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(256)
+warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hinv, int n_h, int H, int W,
+                  int tiles_x, ErodeK ek, float* __restrict__ warped, uint8_t* __restrict__ mask) {
+  __shared__ uint8_t raw[kRawH][kRawW];
+  __shared__ float m[9];
+  const int slot = blockIdx.y;
+  const int img = slot / (n_h + 1), j = slot - img * (n_h + 1);
+  const int tx0 = (blockIdx.x % tiles_x) * kTileW, ty0 = (blockIdx.x / tiles_x) * kTileH;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = tx0 + tx, y = ty0 + ty;
+  const float* src = images + (size_t)img * H * W;
+  const size_t o = ((size_t)slot * H + y) * W + x;
+  if (j == 0) {  // identity forward (export.py:93): the image itself, no mask
+    if (x < W && y < H) {
+      warped[o] = __ldg(&src[(size_t)y * W + x]);
+      mask[o] = 1;
+    }
+    return;
+  }
+  if (threadIdx.x < 9) m[threadIdx.x] = __ldg(&hinv[((size_t)img * n_h + (j - 1)) * 9 + threadIdx.x]);
+  __syncthreads();
+  fill_raw(raw, m, ek, tx0, ty0, H, W);
+  __syncthreads();
+  if (x < W && y < H) {
+    float sx, sy;
+    apply_h(m, (float)x, (float)y, sx, sy);
+    warped[o] = bilinear_zero(src, sx, sy, H, W);
+    mask[o] = (uint8_t)eroded_at(raw, ek, tx, ty);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ hmat, int n_h, int H, int W,
+                    int tiles_x, ErodeK ek, int agg_max, float* __restrict__ out) {
+  extern __shared__ float hs[];  // n_h * 9
+  __shared__ uint8_t raw[2][kRawH][kRawW];
+  const int img = blockIdx.y;
+  const int tx0 = (blockIdx.x % tiles_x) * kTileW, ty0 = (blockIdx.x / tiles_x) * kTileH;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = tx0 + tx, y = ty0 + ty;
+  const bool in_img = x < W && y < H;
+  for (int i = threadIdx.x; i < n_h * 9; i += blockDim.x) hs[i] = __ldg(&hmat[(size_t)img * n_h * 9 + i]);
+  const float* pimg = probs + (size_t)img * (n_h + 1) * H * W;
+  float acc = 0.f, cnt = 1.f, mx = 0.f;
+  if (in_img) {
+    acc = __ldg(&pimg[(size_t)y * W + x]);
+    mx = acc;
+  }
+  __syncthreads();
+  for (int j = 0; j < n_h; ++j) {
+    const float* m = hs + j * 9;
+    uint8_t (*rb)[kRawW] = raw[j & 1];
+    fill_raw(rb, m, ek, tx0, ty0, H, W);
+    __syncthreads();
+    if (in_img) {
+      float v = 0.f;
+      if (eroded_at(rb, ek, tx, ty)) {
+        float sx, sy;
+        apply_h(m, (float)x, (float)y, sx, sy);
+        v = bilinear_zero(pimg + (size_t)(j + 1) * H * W, sx, sy, H, W);
+        acc += v;
+        cnt += 1.f;
+      }
+      mx = fmaxf(mx, v);
+    }
+  }
+  if (in_img) out[((size_t)img * H + y) * W + x] = agg_max ? mx : acc / cnt;
+}
+
+// ---------------- device homography sampler (homographic_augmentation.py:21-106) ----------------
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+struct Rng {
+  uint64_t key, ctr;
+  __device__ double uniform() {  // (0,1)
+    const uint64_t r = splitmix64(key ^ splitmix64(ctr++));
+    return ((double)(r >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  }
+  __device__ double truncnorm(double loc, double scale) {  // scipy.stats.truncnorm(-2, 2, loc, scale)
+    const double lo = 0.022750131948179195, hi = 0.9772498680518208;  // Phi(-2), Phi(2)
+    return loc + scale * normcdfinv(lo + uniform() * (hi - lo));
+  }
+  __device__ int randint(int n) { return min((int)(uniform() * n), n - 1); }
+};
+
+__device__ void inv3x3(const float* a, float* o) {
+  const float c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+  const float det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+  const float id = 1.0f / det;
+  o[0] = c00 * id; o[1] = (a[2] * a[7] - a[1] * a[8]) * id; o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+  o[3] = c01 * id; o[4] = (a[0] * a[8] - a[2] * a[6]) * id; o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+  o[6] = c02 * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+__device__ bool all_in_unit(const double (*p)[2]) {
+  bool ok = true;
+  for (int i = 0; i < 4; ++i) ok = ok && p[i][0] >= 0.0 && p[i][0] <= 1.0 && p[i][1] >= 0.0 && p[i][1] <= 1.0;
+  return ok;
+}
+
+__global__ void sample_homographies_kernel(spn_homography_params prm, uint64_t seed, uint64_t first, int count, int H,
+                                           int W, float* __restrict__ out_h, float* __restrict__ out_hinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Rng rng{splitmix64(seed) ^ splitmix64(0xD1B54A32D192ED03ull * (first + i + 1)), 0};
+  const double pr = prm.patch_ratio, margin = (1.0 - pr) / 2.0;
+  double p1[4][2] = {{margin, margin}, {margin, margin + pr}, {margin + pr, margin + pr}, {margin + pr, margin}};
+  double p2[4][2];
+  for (int k = 0; k < 4; ++k) { p2[k][0] = p1[k][0]; p2[k][1] = p1[k][1]; }
+  if (prm.perspective) {
+    double ax = prm.perspective_amplitude_x, ay = prm.perspective_amplitude_y;
+    if (!prm.allow_artifacts) { ax = fmin(ax, margin); ay = fmin(ay, margin); }
+    const double dy = rng.truncnorm(0.0, ay / 2), dl = rng.truncnorm(0.0, ax / 2), dr = rng.truncnorm(0.0, ax / 2);
+    p2[0][0] += dl; p2[0][1] += dy;
+    p2[1][0] += dl; p2[1][1] -= dy;
+    p2[2][0] += dr; p2[2][1] += dy;
+    p2[3][0] += dr; p2[3][1] -= dy;
+  }
+  if (prm.scaling) {
+    const int ns = min(prm.n_scales, 31);
+    double sc[32];
+    sc[0] = 1.0;
+    for (int k = 1; k <= ns; ++k) sc[k] = rng.truncnorm(1.0, prm.scaling_amplitude / 2);
+    double cx = 0, cy = 0;
+    for (int k = 0; k < 4; ++k) { cx += p2[k][0]; cy += p2[k][1]; }
+    cx /= 4; cy /= 4;
+    int valid[32], nv = 0;
+    for (int k = (prm.allow_artifacts ? 1 : 0); k <= ns; ++k) {
+      double q[4][2];
+      for (int t = 0; t < 4; ++t) { q[t][0] = (p2[t][0] - cx) * sc[k] + cx; q[t][1] = (p2[t][1] - cy) * sc[k] + cy; }
+      if (prm.allow_artifacts || all_in_unit(q)) valid[nv++] = k;
+    }
+    const int idx = nv ? valid[rng.randint(nv)] : 0;
+    for (int t = 0; t < 4; ++t) { p2[t][0] = (p2[t][0] - cx) * sc[idx] + cx; p2[t][1] = (p2[t][1] - cy) * sc[idx] + cy; }
+  }
+  if (prm.translation) {
+    double tminx = 1e30, tminy = 1e30, tmaxx = 1e30, tmaxy = 1e30;
+    for (int t = 0; t < 4; ++t) {
+      tminx = fmin(tminx, p2[t][0]); tminy = fmin(tminy, p2[t][1]);
+      tmaxx = fmin(tmaxx, 1.0 - p2[t][0]); tmaxy = fmin(tmaxy, 1.0 - p2[t][1]);
+    }
+    if (prm.allow_artifacts) {
+      tminx += prm.translation_overflow; tminy += prm.translation_overflow;
+      tmaxx += prm.translation_overflow; tmaxy += prm.translation_overflow;
+    }
+    const double dx = -tminx + rng.uniform() * (tmaxx + tminx), dy = -tminy + rng.uniform() * (tmaxy + tminy);
+    for (int t = 0; t < 4; ++t) { p2[t][0] += dx; p2[t][1] += dy; }
+  }
+  if (prm.rotation) {
+    const int na = min(prm.n_angles, 63);
+    double cx = 0, cy = 0;
+    for (int k = 0; k < 4; ++k) { cx += p2[k][0]; cy += p2[k][1]; }
+    cx /= 4; cy /= 4;
+    int valid[64], nv = 0;
+    for (int k = (prm.allow_artifacts ? 1 : 0); k <= na; ++k) {
+      const double ang = k == 0 ? 0.0 : (na > 1 ? -prm.max_angle + (2.0 * prm.max_angle) * (k - 1) / (na - 1) : -prm.max_angle);
+      const double c = cos(ang), s = sin(ang);
+      double q[4][2];
+      for (int t = 0; t < 4; ++t) {  // (p - c) @ [[cos, -sin], [sin, cos]]
+        const double ux = p2[t][0] - cx, uy = p2[t][1] - cy;
+        q[t][0] = ux * c + uy * s + cx;
+        q[t][1] = -ux * s + uy * c + cy;
+      }
+      if (prm.allow_artifacts || all_in_unit(q)) valid[nv++] = k;
+    }
+    const int idx = nv ? valid[rng.randint(nv)] : 0;
+    const double ang = idx == 0 ? 0.0 : (na > 1 ? -prm.max_angle + (2.0 * prm.max_angle) * (idx - 1) / (na - 1) : -prm.max_angle);
+    const double c = cos(ang), s = sin(ang);
+    for (int t = 0; t < 4; ++t) {
+      const double ux = p2[t][0] - cx, uy = p2[t][1] - cy;
+      p2[t][0] = ux * c + uy * s + cx;
+      p2[t][1] = -ux * s + uy * c + cy;
+    }
+  }
+  // to pixels (x * W, y * H), rounded to fp32 like np.float32(pts) before cv2.getPerspectiveTransform
+  double a[8][9];
+  for (int t = 0; t < 4; ++t) {
+    const double sx = (double)(float)(p1[t][0] * W), sy = (double)(float)(p1[t][1] * H);
+    const double dx = (double)(float)(p2[t][0] * W), dy = (double)(float)(p2[t][1] * H);
+    double* r0 = a[t];
+    double* r1 = a[t + 4];
+    r0[0] = sx; r0[1] = sy; r0[2] = 1; r0[3] = 0; r0[4] = 0; r0[5] = 0; r0[6] = -sx * dx; r0[7] = -sy * dx; r0[8] = dx;
+    r1[0] = 0; r1[1] = 0; r1[2] = 0; r1[3] = sx; r1[4] = sy; r1[5] = 1; r1[6] = -sx * dy; r1[7] = -sy * dy; r1[8] = dy;
+  }
+  for (int c = 0; c < 8; ++c) {  // Gaussian elimination, partial pivoting (cv2 solves with DECOMP_LU)
+    int piv = c;
+    for (int r = c + 1; r < 8; ++r)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    if (piv != c)
+      for (int k = 0; k < 9; ++k) { const double t = a[c][k]; a[c][k] = a[piv][k]; a[piv][k] = t; }
+    const double d = 1.0 / a[c][c];
+    for (int r = c + 1; r < 8; ++r) {
+      const double f = a[r][c] * d;
+      for (int k = c; k < 9; ++k) a[r][k] -= f * a[c][k];
+    }
+  }
+  double sol[8];
+  for (int r = 7; r >= 0; --r) {
+    double s = a[r][8];
+    for (int k = r + 1; k < 8; ++k) s -= a[r][k] * sol[k];
+    sol[r] = s / a[r][r];
+  }
+  float M[9], Hm[9], Hi[9];
+  for (int k = 0; k < 8; ++k) M[k] = (float)sol[k];
+  M[8] = 1.0f;
+  inv3x3(M, Hm);   // homography = torch.inverse(M)           (homographic_augmentation.py:104)
+  inv3x3(Hm, Hi);  // H_inv = torch.inverse(H)                (export.py:49)
+  for (int k = 0; k < 9; ++k) {
+    out_h[(size_t)i * 9 + k] = Hm[k];
+    out_hinv[(size_t)i * 9 + k] = Hi[k];
+  }
+}
+
+__global__ void invert3x3_kernel(const float* __restrict__ in, int count, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float a[9], o[9];
+  for (int k = 0; k < 9; ++k) a[k] = in[(size_t)i * 9 + k];
+  inv3x3(a, o);
+  for (int k = 0; k < 9; ++k) out[(size_t)i * 9 + k] = o[k];
+}
+
+}  // namespace
+
+extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H,
+                              int W, int margin, float* d_warped, uint8_t* d_mask, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_images && d_warped && d_mask, "spn_warp_batch: null pointer");
+  SPN_REQUIRE(n_images > 0 && n_h >= 0 && H > 0 && W > 0, "spn_warp_batch: bad shape");
+  SPN_REQUIRE(n_h == 0 || d_hinv, "spn_warp_batch: d_hinv is null");
+  // the reference's valid_border_margin == 0 path is shape-broken: unsupported
+  SPN_REQUIRE(margin >= 1 && 2 * margin <= kMaxKs, "spn_warp_batch: valid_border_margin must be in [1,%d]", kMaxKs / 2);
+  SPN_REQUIRE((size_t)n_images * (n_h + 1) <= 65535, "spn_warp_batch: too many slots per launch");
+  const ErodeK ek = make_ellipse(margin);
+  const int tiles_x = spn_cdiv(W, kTileW), tiles_y = spn_cdiv(H, kTileH);
+  dim3 grid(tiles_x * tiles_y, n_images * (n_h + 1));
+  warp_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_images, d_hinv, n_h, H, W, tiles_x, ek, d_warped, d_mask);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}
+
+extern "C" int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float* d_h, int n_images, int n_h, int H,
+                                int W, int margin, int aggregation, float* d_out, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_probs && d_out, "spn_ha_aggregate: null pointer");
+  SPN_REQUIRE(n_images > 0 && n_images <= 65535 && n_h >= 0 && H > 0 && W > 0, "spn_ha_aggregate: bad shape");
+  SPN_REQUIRE(n_h == 0 || d_h, "spn_ha_aggregate: d_h is null");
+  SPN_REQUIRE(margin >= 1 && 2 * margin <= kMaxKs, "spn_ha_aggregate: valid_border_margin must be in [1,%d]", kMaxKs / 2);
+  SPN_REQUIRE(aggregation == 0 || aggregation == 1, "spn_ha_aggregate: aggregation must be 0 (sum) or 1 (max)");
+  SPN_REQUIRE(n_h * 9 * sizeof(float) <= 40 * 1024, "spn_ha_aggregate: too many homographies per image");
+  const ErodeK ek = make_ellipse(margin);
+  const int tiles_x = spn_cdiv(W, kTileW), tiles_y = spn_cdiv(H, kTileH);
+  dim3 grid(tiles_x * tiles_y, n_images);
+  ha_aggregate_kernel<<<grid, 256, n_h * 9 * sizeof(float), (cudaStream_t)stream>>>(d_probs, d_h, n_h, H, W, tiles_x, ek,
+                                                                                     aggregation, d_out);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}
+
+extern "C" int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params* params, uint64_t seed,
+                                       uint64_t first_index, int count, int H, int W, float* d_h, float* d_hinv,
+                                       spn_stream stream) {
+  SPN_REQUIRE(ctx && params && d_h && d_hinv, "spn_sample_homographies: null pointer");
+  SPN_REQUIRE(count >= 0 && H > 0 && W > 0, "spn_sample_homographies: bad shape");
+  SPN_REQUIRE(params->n_scales >= 1 && params->n_scales <= 31 && params->n_angles >= 1 && params->n_angles <= 63,
+              "spn_sample_homographies: n_scales must be in [1,31], n_angles in [1,63]");
+  if (count == 0) return SPN_OK;
+  sample_homographies_kernel<<<spn_cdiv(count, 64), 64, 0, (cudaStream_t)stream>>>(*params, seed, first_index, count, H,
+                                                                                    W, d_h, d_hinv);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}
+
+extern "C" int spn_invert3x3(spn_ctx* ctx, const float* d_in, int count, float* d_out, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_in && d_out && count >= 0, "spn_invert3x3: bad argument");
+  if (count == 0) return SPN_OK;
+  invert3x3_kernel<<<spn_cdiv(count, 128), 128, 0, (cudaStream_t)stream>>>(d_in, count, d_out);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}

@@ -1,0 +1,221 @@
+// box_nms + threshold + keypoint compaction, bit-exact with the reference's greedy formulation.
+//
+// Reference: models/model_utils/sp_utils.py:4-28 (box_nms = torchvision.ops.nms over size x size boxes centred
+// on every pixel >= min_prob, optional top-k, scatter), heads.py:41 / export.py:123-125 (threshold + nonzero).
+//
+// torchvision's nms is the sequential greedy algorithm over a stable descending sort.  Because all boxes are
+// the same size and centred on integer pixels, "box j suppresses box i" depends only on the pixel offset, so
+// the greedy result equals the unique fixed point of:
+//     a candidate is KEPT       iff every footprint neighbour that outranks it is SUPPRESSED,
+//     a candidate is SUPPRESSED iff some footprint neighbour is KEPT,
+// with rank = (score desc, row-major index asc).  The kernel iterates that rule to the fixed point with one
+// __syncthreads per round; each round only touches still-undecided pixels.
+// One 1024-thread CTA owns one image, so a batch of B images runs B CTAs concurrently (the export path batches
+// >= 148 images); status bytes live in a caller-invisible scratch buffer and stay L1/L2 resident.
+#include <math.h>
+
+#include "spn_common.cuh"
+
+namespace {
+
+constexpr int kMaxFoot = 288;  // 17x17 - 1 : box size up to 8
+constexpr int kThreads = 1024;
+
+struct NmsFoot {
+  int n;
+  int8_t dy[kMaxFoot];
+  int8_t dx[kMaxFoot];
+};
+
+// IoU test exactly as torchvision computes it in fp32 for boxes [c - s/2, c + s/2] (no +1 on widths).
+bool foot_suppresses(float size, float iou, int dy, int dx) {
+  const float h = size / 2.0f;
+  const float ay1 = 0.0f - h, ax1 = 0.0f - h, ay2 = 0.0f + h, ax2 = 0.0f + h;
+  const float by1 = (float)dy - h, bx1 = (float)dx - h, by2 = (float)dy + h, bx2 = (float)dx + h;
+  const float areaa = (ay2 - ay1) * (ax2 - ax1), areab = (by2 - by1) * (bx2 - bx1);
+  const float yy1 = fmaxf(ay1, by1), xx1 = fmaxf(ax1, bx1), yy2 = fminf(ay2, by2), xx2 = fminf(ax2, bx2);
+  const float w = fmaxf(0.0f, yy2 - yy1), hh = fmaxf(0.0f, xx2 - xx1);
+  const float inter = w * hh;
+  const float ovr = inter / (areaa + areab - inter);
+  return ovr > iou;
+}
+
+__device__ __forceinline__ uint32_t ordered_key(float f) {  // monotone float -> uint
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// exclusive prefix of `flag` over the 1024 threads in thread order; *total gets the block sum. 2 barriers.
+__device__ __forceinline__ int block_excl_scan_flag(bool flag, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int within = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) s_warp[warp] = __popc(bal);
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int c = s_warp[w];
+    if (w < warp) base += c;
+    tot += c;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + within;
+}
+
+__global__ void __launch_bounds__(kThreads)
+box_nms_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ status_all, NmsFoot foot, int H, int W,
+               float min_prob, int top_k, float det_thresh, float* __restrict__ nms_all, int32_t* __restrict__ pred_all,
+               int32_t* __restrict__ kp_all, int32_t* __restrict__ kp_count, int max_kp) {
+  __shared__ int s_warp[kThreads / 32];
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_sel[2];
+  const int b = blockIdx.x;
+  const int P = H * W;
+  const float* prob = prob_all + (size_t)b * P;
+  volatile uint8_t* status = status_all + (size_t)b * P;
+  const int tid = threadIdx.x;
+
+  for (int p = tid; p < P; p += kThreads) status[p] = (__ldg(&prob[p]) >= min_prob) ? 1 : 0;
+  __syncthreads();
+
+  // ---- greedy NMS as a parallel fixed point ----
+  while (true) {
+    bool pending = false;
+    for (int p = tid; p < P; p += kThreads) {
+      if (status[p] != 1) continue;
+      const int y = p / W, x = p - y * W;
+      const float sp = __ldg(&prob[p]);
+      int res = 2;
+      for (int k = 0; k < foot.n; ++k) {
+        const int yy = y + foot.dy[k], xx = x + foot.dx[k];
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const int q = yy * W + xx;
+        const uint8_t st = status[q];
+        if (st == 2) { res = 0; break; }
+        if (st == 1) {
+          const float sq = __ldg(&prob[q]);
+          if (sq > sp || (sq == sp && q < p)) res = 1;
+        }
+      }
+      if (res == 1) pending = true;
+      else status[p] = (uint8_t)res;
+    }
+    if (!__syncthreads_or(pending)) break;
+  }
+
+  // ---- optional top-k over the survivors: (score desc, index asc) ----
+  if (top_k > 0) {
+    int mine = 0;
+    for (int p = tid; p < P; p += kThreads) mine += (status[p] == 2);
+    // block sum of kept
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = mine;
+    __syncthreads();
+    int kept = 0;
+    for (int w = 0; w < kThreads / 32; ++w) kept += s_warp[w];
+    __syncthreads();
+    if (kept > top_k) {
+      uint32_t prefix = 0, maskbits = 0;
+      unsigned want = (unsigned)top_k;  // rank (1-based, descending) of the threshold element
+      for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        for (int p = tid; p < P; p += kThreads) {
+          if (status[p] != 2) continue;
+          const uint32_t key = ordered_key(__ldg(&prob[p]));
+          if ((key & maskbits) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          unsigned cum = 0;
+          int bin = 255;
+          for (; bin > 0; --bin) {
+            if (cum + s_hist[bin] >= want) break;
+            cum += s_hist[bin];
+          }
+          s_sel[0] = (unsigned)bin;
+          s_sel[1] = want - cum;
+        }
+        __syncthreads();
+        prefix |= s_sel[0] << shift;
+        maskbits |= 0xffu << shift;
+        want = s_sel[1];
+        __syncthreads();
+      }
+      // prefix = key of the top_k-th survivor; keep keys > prefix, and the first `want` equal keys in index order
+      int tie_base = 0;
+      for (int base = 0; base < P; base += kThreads) {
+        const int p = base + tid;
+        bool tie = false;
+        if (p < P && status[p] == 2) {
+          const uint32_t key = ordered_key(__ldg(&prob[p]));
+          if (key < prefix) status[p] = 0;
+          tie = (key == prefix);
+        }
+        int tot;
+        const int rank = block_excl_scan_flag(tie, s_warp, &tot);
+        if (tie && (unsigned)(tie_base + rank) >= want) status[p] = 0;
+        tie_base += tot;
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- outputs: scattered map, thresholded map, row-major keypoint list ----
+  float* nms = nms_all ? nms_all + (size_t)b * P : nullptr;
+  int32_t* pred = pred_all ? pred_all + (size_t)b * P : nullptr;
+  int32_t* kp = kp_all ? kp_all + (size_t)b * max_kp * 2 : nullptr;
+  int kp_base = 0;
+  for (int base = 0; base < P; base += kThreads) {
+    const int p = base + tid;
+    bool is_kp = false;
+    if (p < P) {
+      const float v = (status[p] == 2) ? __ldg(&prob[p]) : 0.0f;
+      is_kp = v >= det_thresh;
+      if (nms) nms[p] = v;
+      if (pred) pred[p] = is_kp ? 1 : 0;
+    }
+    if (kp || kp_count) {
+      int tot;
+      const int rank = block_excl_scan_flag(is_kp, s_warp, &tot);
+      if (is_kp && kp && kp_base + rank < max_kp) {
+        const int y = p / W;
+        kp[2 * (kp_base + rank)] = y;
+        kp[2 * (kp_base + rank) + 1] = p - y * W;
+      }
+      kp_base += tot;
+    }
+  }
+  if (kp_count && tid == 0) kp_count[b] = kp_base;
+}
+
+}  // namespace
+
+extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H, int W, float size, float iou,
+                                float min_prob, int top_k, float det_thresh, float* d_nms, int32_t* d_pred,
+                                int32_t* d_kp, int32_t* d_kp_count, int max_kp, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_prob, "spn_box_nms_topk: null pointer");
+  SPN_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "spn_box_nms_topk: bad shape");
+  SPN_REQUIRE(size > 0.f && size <= 8.f, "spn_box_nms_topk: box size must be in (0, 8]");
+  SPN_REQUIRE(!d_kp || max_kp > 0, "spn_box_nms_topk: max_kp must be > 0 when d_kp is given");
+  NmsFoot foot;
+  memset(&foot, 0, sizeof(foot));
+  const int r = (int)ceilf(size);
+  for (int dy = -r; dy <= r; ++dy)
+    for (int dx = -r; dx <= r; ++dx)
+      if ((dy || dx) && foot_suppresses(size, iou, dy, dx)) {
+        if (foot.n >= kMaxFoot) { spn_set_error("spn_box_nms_topk: footprint too large"); return SPN_E_INVALID; }
+        foot.dy[foot.n] = (int8_t)dy;
+        foot.dx[foot.n] = (int8_t)dx;
+        foot.n++;
+      }
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = spn_ensure_aux(ctx, (size_t)B * H * W, s);
+  if (rc) return rc;
+  box_nms_kernel<<<B, kThreads, 0, s>>>(d_prob, (uint8_t*)ctx->aux, foot, H, W, min_prob, top_k, det_thresh, d_nms,
+                                        d_pred, d_kp, d_kp_count, max_kp);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}

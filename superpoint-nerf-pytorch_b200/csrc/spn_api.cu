@@ -1,0 +1,234 @@
+// C-ABI entry points (include/spn_b200.h): context, weight packing, encoder / head orchestration.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "spn_common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void spn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* spn_last_error(void) { return g_err; }
+extern "C" int spn_version(void) { return 100; }
+
+static int grow(char** buf, size_t* have, size_t need, cudaStream_t s) {
+  if (need <= *have) return SPN_OK;
+  // growing the workspace is the one place that synchronises (first call with a larger shape)
+  SPN_CUDA(cudaStreamSynchronize(s));
+  if (*buf) SPN_CUDA(cudaFree(*buf));
+  *buf = nullptr;
+  *have = 0;
+  const size_t sz = (need + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+  cudaError_t e = cudaMalloc((void**)buf, sz);
+  if (e != cudaSuccess) {
+    spn_set_error("cudaMalloc(%zu) failed: %s", sz, cudaGetErrorString(e));
+    return SPN_E_NOMEM;
+  }
+  *have = sz;
+  return SPN_OK;
+}
+
+int spn_ensure_ws(spn_ctx* ctx, size_t bytes, cudaStream_t s) {
+  const char* old = ctx->ws;
+  int rc = grow(&ctx->ws, &ctx->ws_bytes, bytes, s);
+  if (ctx->ws != old) ctx->feat_mode = -1;  // feature map lived in the old workspace
+  return rc;
+}
+int spn_ensure_aux(spn_ctx* ctx, size_t bytes, cudaStream_t s) { return grow(&ctx->aux, &ctx->aux_bytes, bytes, s); }
+
+extern "C" int spn_create(spn_ctx** out, int device) {
+  if (!out) { spn_set_error("spn_create: out is null"); return SPN_E_INVALID; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    spn_set_error("spn_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    return SPN_E_CUDA;
+  }
+  SPN_REQUIRE(device >= 0 && device < n, "spn_create: device %d out of range [0,%d)", device, n);
+  SPN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SPN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    spn_set_error("spn_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    return SPN_E_CUDA;
+  }
+  spn_ctx* c = new spn_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return SPN_OK;
+}
+
+extern "C" int spn_destroy(spn_ctx* ctx) {
+  if (!ctx) return SPN_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  spn_tc_destroy(ctx);
+  for (auto& L : ctx->layers) {
+    if (L.w32) cudaFree(L.w32);
+    if (L.bias) cudaFree(L.bias);
+    for (auto& p : L.w16) if (p) cudaFree(p);
+  }
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->aux) cudaFree(ctx->aux);
+  delete ctx;
+  return SPN_OK;
+}
+
+extern "C" int64_t spn_launch_count(spn_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int spn_pack_weights(spn_ctx* ctx, int layer, const float* h_w, const float* h_b, const float* h_gamma,
+                                const float* h_beta, const float* h_mean, const float* h_var, float eps, int cout,
+                                int cin, int ksize, spn_stream stream) {
+  SPN_REQUIRE(ctx && h_w, "spn_pack_weights: null pointer");
+  SPN_REQUIRE(layer >= 0 && layer < SPN_NUM_LAYERS, "spn_pack_weights: layer %d out of range", layer);
+  SPN_REQUIRE((ksize == 1 || ksize == 3) && cin > 0 && cout > 0, "spn_pack_weights: unsupported conv %dx%d %d->%d", ksize, ksize, cin, cout);
+  cudaStream_t s = (cudaStream_t)stream;
+  SPN_CUDA(cudaSetDevice(ctx->device));
+  const int taps = ksize * ksize;
+  const int cout_pad = (cout + 15) / 16 * 16;
+  // fold eval-mode BatchNorm (VGG_Backbone.py:28-29): y = (conv + b - mean) * gamma / sqrt(var + eps) + beta
+  std::vector<float> wf((size_t)cout * cin * taps), bf(cout);
+  std::vector<float> wpk((size_t)cin * taps * cout_pad, 0.f), bpk(cout_pad, 0.f);
+  for (int co = 0; co < cout; ++co) {
+    double scale = 1.0, shift = 0.0;
+    const double b0 = h_b ? (double)h_b[co] : 0.0;
+    if (h_gamma && h_beta && h_mean && h_var) {
+      scale = (double)h_gamma[co] / sqrt((double)h_var[co] + (double)eps);
+      shift = (double)h_beta[co] - (double)h_mean[co] * scale;
+    }
+    bf[co] = (float)(b0 * scale + shift);
+    bpk[co] = bf[co];
+    for (int ci = 0; ci < cin; ++ci)
+      for (int t = 0; t < taps; ++t) {
+        const float v = (float)((double)h_w[((size_t)co * cin + ci) * taps + t] * scale);
+        wf[((size_t)co * cin + ci) * taps + t] = v;
+        wpk[((size_t)ci * taps + t) * cout_pad + co] = v;
+      }
+  }
+  SpnLayer& L = ctx->layers[layer];
+  SPN_CUDA(cudaStreamSynchronize(s));
+  if (L.w32) { cudaFree(L.w32); L.w32 = nullptr; }
+  if (L.bias) { cudaFree(L.bias); L.bias = nullptr; }
+  SPN_CUDA(cudaMalloc((void**)&L.w32, wpk.size() * sizeof(float)));
+  SPN_CUDA(cudaMalloc((void**)&L.bias, bpk.size() * sizeof(float)));
+  SPN_CUDA(cudaMemcpy(L.w32, wpk.data(), wpk.size() * sizeof(float), cudaMemcpyHostToDevice));
+  SPN_CUDA(cudaMemcpy(L.bias, bpk.data(), bpk.size() * sizeof(float), cudaMemcpyHostToDevice));
+  L.cin = cin; L.cout = cout; L.ks = ksize; L.cout_pad = cout_pad;
+  ctx->feat_mode = -1;
+  return spn_tc_pack_layer(ctx, layer, wf.data(), bf.data(), s);
+}
+
+// workspace carve-up for the strict (NCHW fp32) path, in floats
+struct Fp32Plan {
+  size_t bufA, bufB, feat, total;
+};
+static Fp32Plan fp32_plan(int B, int H, int W) {
+  Fp32Plan p;
+  const size_t hw = (size_t)H * W;
+  p.bufA = (size_t)B * 64 * hw;      // block_1 out (largest), later layers ping-pong
+  p.bufB = (size_t)B * 64 * hw / 4;  // pooled outputs
+  p.feat = (size_t)B * 128 * hw / 64;
+  p.total = p.bufA + p.bufB + p.feat + (size_t)B * 80 * hw / 64;  // + logits scratch
+  return p;
+}
+
+static int check_image_shape(int B, int H, int W) {
+  SPN_REQUIRE(B > 0 && B <= 65535, "batch %d out of range", B);
+  SPN_REQUIRE(H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "H and W must be positive multiples of 8 (got %dx%d)", H, W);
+  return SPN_OK;
+}
+
+extern "C" int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode,
+                                   spn_stream stream) {
+  SPN_REQUIRE(ctx && d_images, "spn_encoder_forward: null pointer");
+  int rc = check_image_shape(B, H, W);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  SPN_CUDA(cudaSetDevice(ctx->device));
+  for (int l = SPN_L_BLOCK1; l <= SPN_L_BLOCK8; ++l)
+    if (!ctx->layers[l].w32) { spn_set_error("spn_encoder_forward: layer %d has no weights", l); return SPN_E_STATE; }
+  if (mode == SPN_MODE_F16 || mode == SPN_MODE_BF16) {
+    rc = spn_tc_encoder(ctx, d_images, B, H, W, mode, s);
+    if (rc) return rc;
+  } else {
+    SPN_REQUIRE(mode == SPN_MODE_FP32, "spn_encoder_forward: unknown mode %d", mode);
+    const Fp32Plan p = fp32_plan(B, H, W);
+    rc = spn_ensure_ws(ctx, p.total * sizeof(float), s);
+    if (rc) return rc;
+    float* A = (float*)ctx->ws;
+    float* Bq = A + p.bufA;
+    float* F = Bq + p.bufB;
+    // VGG_BACKBONE.forward (VGG_Backbone.py:60-71): pools after blocks 2, 4, 6
+    if ((rc = spn_conv_fp32(ctx, 0, d_images, A, B, H, W, true, false, s))) return rc;
+    if ((rc = spn_conv_fp32(ctx, 1, A, Bq, B, H, W, true, true, s))) return rc;
+    if ((rc = spn_conv_fp32(ctx, 2, Bq, A, B, H / 2, W / 2, true, false, s))) return rc;
+    if ((rc = spn_conv_fp32(ctx, 3, A, Bq, B, H / 2, W / 2, true, true, s))) return rc;
+    if ((rc = spn_conv_fp32(ctx, 4, Bq, A, B, H / 4, W / 4, true, false, s))) return rc;
+    if ((rc = spn_conv_fp32(ctx, 5, A, Bq, B, H / 4, W / 4, true, true, s))) return rc;
+    if ((rc = spn_conv_fp32(ctx, 6, Bq, A, B, H / 8, W / 8, true, false, s))) return rc;
+    if ((rc = spn_conv_fp32(ctx, 7, A, F, B, H / 8, W / 8, true, false, s))) return rc;
+    ctx->feat = F;
+  }
+  ctx->feat_B = B; ctx->feat_H = H; ctx->feat_W = W; ctx->feat_mode = mode;
+  return SPN_OK;
+}
+
+static int check_feat(spn_ctx* ctx, int B, int H, int W, int mode, const char* who) {
+  if (ctx->feat_mode != mode || ctx->feat_B != B || ctx->feat_H != H || ctx->feat_W != W) {
+    spn_set_error("%s: no feature map for B=%d H=%d W=%d mode=%d (call spn_encoder_forward first)", who, B, H, W, mode);
+    return SPN_E_STATE;
+  }
+  return SPN_OK;
+}
+
+extern "C" int spn_detector_head_forward(spn_ctx* ctx, int B, int H, int W, int mode, const uint8_t* d_mask,
+                                         float* d_logits, float* d_prob, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_prob, "spn_detector_head_forward: null pointer");
+  int rc = check_feat(ctx, B, H, W, mode, "spn_detector_head_forward");
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  SPN_CUDA(cudaSetDevice(ctx->device));
+  const SpnLayer& Pb = ctx->layers[SPN_L_CONVPB];
+  if (!ctx->layers[SPN_L_CONVPA].w32 || !Pb.w32) { spn_set_error("detector head has no weights"); return SPN_E_STATE; }
+  SPN_REQUIRE(Pb.cout == 65, "detector head must have 65 output channels (grid_size 8), got %d", Pb.cout);
+  const int Hc = H / 8, Wc = W / 8;
+  float* logits = d_logits;
+  if (mode == SPN_MODE_FP32) {
+    const Fp32Plan p = fp32_plan(B, H, W);
+    float* A = (float*)ctx->ws;
+    if (!logits) logits = A + p.bufA + p.bufB + p.feat;
+    if ((rc = spn_conv_fp32(ctx, SPN_L_CONVPA, (const float*)ctx->feat, A, B, Hc, Wc, true, false, s))) return rc;
+    if ((rc = spn_conv_fp32(ctx, SPN_L_CONVPB, A, logits, B, Hc, Wc, false, false, s))) return rc;
+  } else {
+    if ((rc = spn_tc_detector_head(ctx, B, H, W, mode, logits, s))) return rc;
+    if (!logits) return SPN_OK;  // unreachable: tc path always materialises logits (see conv_tc.cu)
+  }
+  return spn_softmax_d2s(ctx, logits, B, Hc, Wc, d_mask, d_prob, s);
+}
+
+extern "C" int spn_descriptor_head_forward(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw,
+                                           spn_stream stream) {
+  SPN_REQUIRE(ctx && d_desc_raw, "spn_descriptor_head_forward: null pointer");
+  int rc = check_feat(ctx, B, H, W, mode, "spn_descriptor_head_forward");
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  SPN_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->layers[SPN_L_CONVDA].w32 || !ctx->layers[SPN_L_CONVDB].w32) {
+    spn_set_error("descriptor head has no weights (model_name != 'superpoint'?)");
+    return SPN_E_STATE;
+  }
+  const int Hc = H / 8, Wc = W / 8;
+  if (mode == SPN_MODE_FP32) {
+    float* A = (float*)ctx->ws;
+    if ((rc = spn_conv_fp32(ctx, SPN_L_CONVDA, (const float*)ctx->feat, A, B, Hc, Wc, true, false, s))) return rc;
+    return spn_conv_fp32(ctx, SPN_L_CONVDB, A, d_desc_raw, B, Hc, Wc, false, false, s);
+  }
+  return spn_tc_descriptor_head(ctx, B, H, W, mode, d_desc_raw, s);
+}

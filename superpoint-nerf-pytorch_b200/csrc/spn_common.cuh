@@ -1,0 +1,79 @@
+// Shared declarations for the sm_100a kernels behind include/spn_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/spn_b200.h"
+
+struct SpnLayer {
+  int cin = 0, cout = 0, ks = 0, cout_pad = 0;
+  float* w32 = nullptr;    // [cin][ks*ks][cout_pad] fp32, BN folded
+  float* bias = nullptr;   // [cout_pad] fp32, BN folded
+  void* w16[2] = {nullptr, nullptr};  // tcgen05 operand-B images (fp16, bf16), see conv_tc.cu
+};
+
+struct spn_ctx {
+  int device = 0;
+  int sm_count = 148;
+  SpnLayer layers[SPN_NUM_LAYERS];
+  char* ws = nullptr;       // activation workspace
+  size_t ws_bytes = 0;
+  char* aux = nullptr;      // small scratch (nms status, ...)
+  size_t aux_bytes = 0;
+  // feature map state left by spn_encoder_forward
+  int feat_B = 0, feat_H = 0, feat_W = 0, feat_mode = -1;
+  void* feat = nullptr;     // points into ws
+  int64_t launches = 0;
+  void* tc = nullptr;       // tcgen05 path state (conv_tc.cu)
+};
+
+void spn_set_error(const char* fmt, ...);
+
+#define SPN_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      spn_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+      return SPN_E_CUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+#define SPN_CHECK_LAUNCH(ctx)                                                                  \
+  do {                                                                                         \
+    (ctx)->launches++;                                                                         \
+    cudaError_t e_ = cudaGetLastError();                                                       \
+    if (e_ != cudaSuccess) {                                                                   \
+      spn_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_));  \
+      return SPN_E_CUDA;                                                                       \
+    }                                                                                          \
+  } while (0)
+
+#define SPN_REQUIRE(cond, ...)                                                                 \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      spn_set_error(__VA_ARGS__);                                                              \
+      return SPN_E_INVALID;                                                                    \
+    }                                                                                          \
+  } while (0)
+
+int spn_ensure_ws(spn_ctx* ctx, size_t bytes, cudaStream_t s);
+int spn_ensure_aux(spn_ctx* ctx, size_t bytes, cudaStream_t s);
+
+// ---- kernels implemented in the other translation units ----
+int spn_conv_fp32(spn_ctx* ctx, int layer, const float* in, float* out, int B, int H, int W, bool relu, bool pool,
+                  cudaStream_t s);
+int spn_softmax_d2s(spn_ctx* ctx, const float* logits, int B, int Hc, int Wc, const uint8_t* mask, float* prob,
+                    cudaStream_t s);
+
+// tcgen05 path (conv_tc.cu)
+int spn_tc_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float* h_bfold, cudaStream_t s);
+int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode, cudaStream_t s);
+int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_logits, cudaStream_t s);
+int spn_tc_descriptor_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw, cudaStream_t s);
+void spn_tc_destroy(spn_ctx* ctx);
+
+static inline int spn_cdiv(int a, int b) { return (a + b - 1) / b; }

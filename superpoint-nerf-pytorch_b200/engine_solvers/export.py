@@ -1,0 +1,201 @@
+"""Export tasks with the reference's class API (engine_solvers/export.py:17-222): the constructor runs the task.
+
+ExportDetections              homography-adaptation pseudo-labels -> <EXPER_PATH>/outputs/<experiment>/<split>/<name>.npy
+Export_Hpatches_Repeatability two forwards per pair               -> <EXPER_PATH>/repeatability/<experiment>/<name>.npz
+Export_Hpatches_Descriptors   + dense descriptors (H,W,256)       -> <EXPER_PATH>/descriptors/<experiment>/<name>.npz
+
+What changes underneath: the 99 sequential batch-1 steps of the reference (export.py:103-104) become ONE batched
+pass per group of images - warp_batch -> encoder/head over all (image, homography) pairs -> fused inverse-warp
+aggregation -> NMS/threshold/compaction - every stage a kernel behind include/spn_b200.h.  The in-model box_nms
+whose result export.py:69 discards is not computed.
+
+Extension keys under ``homography_adaptation`` (optional): ``sampler`` 'device' (default, spn_sample_homographies)
+or 'numpy' (the reference's host sampler and RNG order), ``seed``, ``images_per_launch`` (default 1),
+``max_forwards`` (forwards per encoder launch, default 128).
+"""
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import settings
+from ..data.data_utils.homographic_augmentation import Homographic_aug
+from ..utils.train_utils import move_to_device
+
+try:
+    from tqdm import tqdm
+except ImportError:  # pragma: no cover
+    def tqdm(it, **kw):
+        return it
+
+
+class HomographyAdaptation:
+    """Batched ExportDetections.step/homography_adaptation (export.py:42-125) for a group of images."""
+
+    def __init__(self, config, model, device="cuda"):
+        self.config = config
+        self.ha = config["homography_adaptation"]
+        self.dh = config["model"]["detector_head"]
+        self.model = model.eval()
+        self.device = device
+        self.sampler = Homographic_aug(self.ha, device)
+        self.max_forwards = int(self.ha.get("max_forwards", 128))
+        self.seed = int(self.ha.get("seed", 0))
+        if not self.ha["valid_border_margin"]:
+            # the reference's margin-0 path is shape-broken (mask stays 4-D)
+            raise ValueError("homography_adaptation.valid_border_margin must be >= 1")
+
+    def _homographies(self, NI, n_h, H, W, first_index):
+        if self.ha.get("sampler", "device") == "numpy":
+            hs = [self.sampler.sample_homography((H, W), **self.ha["params"]) for _ in range(NI * n_h)]
+            return torch.cat(hs).view(NI, n_h, 3, 3).contiguous()
+        h, _ = self.sampler.sample_homographies_device((H, W), NI * n_h, seed=self.seed, first_index=first_index * n_h)
+        return h.view(NI, n_h, 3, 3)
+
+    @torch.no_grad()
+    def heatmaps(self, images, homographies=None, enable_HA=True, first_index=0):
+        """images (NI,1,H,W) CUDA fp32 -> (aggregated heatmap (NI,H,W), homographies used (NI,n_h,3,3) or None)."""
+        NI, _, H, W = images.shape
+        ctx = self.model.native()
+        imgs = images.detach().to(torch.float32).contiguous().view(NI, H, W)
+        if not enable_HA:
+            return self.model.prob_heatmap(imgs), None
+        n_h = int(self.ha["num"]) - 1
+        if n_h == 0:
+            return self.model.prob_heatmap(imgs), None
+        if homographies is None:
+            homographies = self._homographies(NI, n_h, H, W, first_index)
+        h = homographies.to(self.device, torch.float32).contiguous().view(NI, n_h, 3, 3)
+        hinv = ctx.invert3x3(h)                                                  # export.py:49
+        warped, mask = ctx.warp_batch(imgs, hinv, self.ha["valid_border_margin"])  # export.py:51-66
+        B = NI * (n_h + 1)
+        probs = torch.empty((B, H, W), dtype=torch.float32, device=imgs.device)
+        for s in range(0, B, self.max_forwards):                                 # export.py:69-70
+            e = min(B, s + self.max_forwards)
+            self.model.prob_heatmap(warped[s:e], mask=mask[s:e], out=probs[s:e])
+        agg = ctx.ha_aggregate(probs.view(NI, n_h + 1, H, W), h, self.ha["valid_border_margin"],
+                               self.ha["aggregation"])                           # export.py:72-77,106-114
+        return agg, h
+
+    @torch.no_grad()
+    def keypoints(self, heat):
+        """box_nms + threshold + nonzero (export.py:116-125) -> list of (N,2) int64 numpy arrays (row, col)."""
+        ctx = self.model.native()
+        NI, H, W = heat.shape
+        max_kp = min(H * W, 16384)
+        while True:
+            r = ctx.box_nms(heat, float(self.dh["nms"]), 0.1, float(self.dh["det_thresh"]), int(self.dh["top_k"]),
+                            det_thresh=float(self.dh["det_thresh"]), want_map=False, max_kp=max_kp)
+            counts = r["kp_count"].cpu().numpy()
+            if counts.max(initial=0) <= max_kp:
+                break
+            max_kp = int(counts.max())
+        kp = r["kp"].cpu().numpy()
+        return [kp[i, :counts[i]].astype(np.int64) for i in range(NI)]
+
+    def __call__(self, images, homographies=None, enable_HA=True, first_index=0):
+        heat, _ = self.heatmaps(images, homographies, enable_HA, first_index)
+        return self.keypoints(heat)
+
+
+class ExportDetections:
+    def __init__(self, config, model, dataloader, split, enable_HA, device):
+        self.config = config
+        self.model = model.eval()
+        self.dataloader = dataloader
+        self.split = split
+        self.enable_HA = enable_HA
+        if self.enable_HA:
+            print("\033[92m✅ Homography Adaptation enabled \033[0m")
+        self.device = device
+        self.output_dir = self._init_output_dir()
+        self.engine = HomographyAdaptation(config, model, device)
+        self.one_homography = self.engine.sampler
+        self.homography_adaptation()
+
+    def _init_output_dir(self):
+        out = Path(settings.EXPER_PATH, "outputs", self.config["data"]["experiment_name"], self.split)
+        os.makedirs(out, exist_ok=True)
+        return out
+
+    def _flush(self, group, index):
+        if not group:
+            return
+        images = torch.cat([g[1] for g in group], dim=0)
+        kps = self.engine(images, enable_HA=self.enable_HA, first_index=index)
+        for (path, _), kp in zip(group, kps):
+            np.save(path, kp)
+
+    @torch.no_grad()
+    def homography_adaptation(self):
+        per_launch = int(self.config["homography_adaptation"].get("images_per_launch", 1))
+        group, done = [], 0
+        for data in tqdm(self.dataloader, desc="Exporting detections", colour="green"):
+            name = data["name"][0]
+            save_path = Path(self.output_dir, f"{name}.npy")
+            if save_path.exists():                     # resume by file existence (export.py:89-91)
+                continue
+            image = move_to_device(data["raw"]["image"], self.device)
+            if group and group[0][1].shape != image.shape:
+                self._flush(group, done)
+                done += len(group)
+                group = []
+            group.append((save_path, image))
+            if len(group) >= per_launch:
+                self._flush(group, done)
+                done += len(group)
+                group = []
+        self._flush(group, done)
+
+
+def _np(t):
+    return t.squeeze().cpu().numpy()
+
+
+class Export_Hpatches_Repeatability:
+    def __init__(self, config, model, dataloader, device):
+        self.config = config
+        self.model = model.eval()
+        self.dataloader = dataloader
+        self.device = device
+        self.output_dir = Path(settings.EXPER_PATH, "repeatability", config["data"]["experiment_name"])
+        os.makedirs(self.output_dir, exist_ok=True)
+        self.export_repeatability()
+
+    @torch.no_grad()
+    def export_repeatability(self):
+        for i, data in enumerate(tqdm(self.dataloader, desc="Exporting repeatability detections", colour="green")):
+            data = move_to_device(data, self.device)
+            both = torch.cat([data["image"], data["warped_image"]], dim=0)  # one batched forward for the pair
+            probs = self.model(both)["detector_output"]["prob_heatmap_nms"]
+            output = {"image": _np(data["image"]), "warped_image": _np(data["warped_image"]),
+                      "prob": _np(probs[0]), "warped_prob": _np(probs[1]), "homography": _np(data["homography"])}
+            filename = data["name"][0] if "name" in data else str(i)
+            np.savez_compressed(Path(self.output_dir, f"{filename}.npz"), **output)
+
+
+class Export_Hpatches_Descriptors:
+    def __init__(self, config, model, dataloader, device):
+        self.config = config
+        self.model = model.eval()
+        self.dataloader = dataloader
+        self.device = device
+        self.output_dir = Path(settings.EXPER_PATH, "descriptors", config["data"]["experiment_name"])
+        os.makedirs(self.output_dir, exist_ok=True)
+        self.export_descriptors()
+
+    @torch.no_grad()
+    def export_descriptors(self):
+        for i, data in enumerate(tqdm(self.dataloader, desc="Exporting HPatches descriptors", colour="green")):
+            data = move_to_device(data, self.device)
+            both = torch.cat([data["image"], data["warped_image"]], dim=0)
+            out = self.model(both)
+            probs = out["detector_output"]["prob_heatmap_nms"]
+            desc = out["descriptor_output"]["desc"]
+            output = {"image": _np(data["image"]), "warped_image": _np(data["warped_image"]),
+                      "prob": _np(probs[0]), "warped_prob": _np(probs[1]),
+                      "desc": desc[0].cpu().numpy().transpose(1, 2, 0), "warped_desc": desc[1].cpu().numpy().transpose(1, 2, 0),
+                      "homography": _np(data["homography"])}
+            filename = data["name"][0] if "name" in data else str(i)
+            np.savez_compressed(Path(self.output_dir, f"{filename}.npz"), **output)

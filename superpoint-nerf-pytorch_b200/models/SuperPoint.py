@@ -1,0 +1,138 @@
+"""Drop-in for the reference's ``models/SuperPoint.py:5-30`` (+ VGG_Backbone.py, heads.py): same constructor
+config, same state-dict keys and shapes, same output dictionary - computed by the sm_100a kernels.
+
+The nn.Conv2d / nn.BatchNorm2d sub-modules only *hold* the parameters (so ``state_dict`` /
+``load_state_dict`` / ``.to`` behave like the reference, engine.py:108-117); forward never calls them.
+Inference only (the reference's export tasks call ``model.eval()``, export.py:21): BN uses running stats.
+
+Extension keys (all optional) in the ``model`` config: ``precision`` in {'fp32','f16','bf16'} (default from
+$SPN_B200_PRECISION, else 'fp32'), ``dense_desc`` (default True, as the reference).
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from .._native import MODES, Context, NativeError
+
+
+class _Block(nn.Module):
+    """Parameter holder with the reference's VGG_Block attribute names (VGG_Backbone.py:11-14)."""
+
+    def __init__(self, cin, cout, k=3):
+        super().__init__()
+        self.conv2d = nn.Conv2d(cin, cout, kernel_size=k, stride=1, padding=k // 2)
+        self.norm = nn.BatchNorm2d(cout)
+
+
+class _Backbone(nn.Module):
+    def __init__(self, cn):
+        super().__init__()
+        dims = [1] + list(cn)
+        for i in range(8):
+            setattr(self, f"block_{i + 1}", _Block(dims[i], dims[i + 1]))
+
+
+class _DetectorHead(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.config = cfg
+        self.convPa = _Block(cfg["detector_dim"][0], cfg["detector_dim"][1])
+        self.convPb = _Block(cfg["detector_dim"][1], cfg["grid_size"] ** 2 + 1, k=1)
+
+
+class _DescriptorHead(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.config = cfg
+        self.convDa = _Block(cfg["descriptor_dim"][0], cfg["descriptor_dim"][1])
+        self.convDb = _Block(cfg["descriptor_dim"][1], cfg["descriptor_dim"][1], k=1)
+
+
+class SuperPoint(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        if list(config["vgg_cn"]) != [64, 64, 64, 64, 128, 128, 128, 128]:
+            raise ValueError("only the reference's vgg_cn [64,64,64,64,128,128,128,128] is supported")
+        if config["detector_head"]["grid_size"] != 8 or list(config["detector_head"]["detector_dim"]) != [128, 256]:
+            raise ValueError("only grid_size 8 / detector_dim [128,256] is supported")
+        self.backbone = _Backbone(config["vgg_cn"])
+        self.detector_head = _DetectorHead(config["detector_head"])
+        if config["model_name"].lower() == "superpoint":
+            if list(config["descriptor_head"]["descriptor_dim"]) != [128, 256] or config["descriptor_head"]["grid_size"] != 8:
+                raise ValueError("only descriptor_dim [128,256] / grid_size 8 is supported")
+            self.descriptor_head = _DescriptorHead(config["descriptor_head"])
+        prec = config.get("precision", os.environ.get("SPN_B200_PRECISION", "fp32"))
+        if prec not in MODES:
+            raise ValueError(f"precision must be one of {sorted(MODES)}, got {prec!r}")
+        self.mode = MODES[prec]
+        self._ctx = None
+        self._packed_key = None
+
+    # ---- native state ----------------------------------------------------------------------------
+    def _weights_key(self):
+        return tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict(keep_vars=True).items())
+
+    def native(self) -> Context:
+        """The Context holding this model's packed weights (re-packed when parameters change)."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise NativeError("SuperPoint (b200) runs on CUDA only: move the model with .to('cuda') (no CPU fallback)")
+        if self._ctx is None or self._ctx.device != (dev.index or 0):
+            with torch.cuda.device(dev):
+                self._ctx = Context(dev.index or 0)
+            self._packed_key = None
+        key = self._weights_key()
+        if key != self._packed_key:
+            with torch.cuda.device(dev):
+                self._ctx.load_state_dict(self.state_dict())
+            self._packed_key = key
+        return self._ctx
+
+    def train(self, mode=True):
+        if mode:
+            raise NativeError("the b200 SuperPoint is inference-only (training is out of scope, SURVEY.md section 2 #8)")
+        return super().train(False)
+
+    # ---- forward (models/SuperPoint.py:17-30) ----------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, mask=None):
+        if not (torch.is_tensor(x) and x.is_cuda):
+            raise NativeError("input must be a CUDA tensor (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError(f"expected (B,1,H,W), got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        ctx = self.native()
+        dh = self.detector_head.config
+        with torch.cuda.device(x.device):
+            img = x.detach().to(torch.float32).contiguous().view(B, H, W)
+            ctx.encoder_forward(img, self.mode)
+            prob, logits = ctx.detector_head_forward(B, H, W, self.mode, mask=mask, want_logits=True)
+            det = {"logits": logits, "prob_heatmap": prob}
+            if dh["nms"]:
+                r = ctx.box_nms(prob, float(dh["nms"]), 0.1, float(dh["det_thresh"]), int(dh["top_k"]),
+                                det_thresh=float(dh["det_thresh"]), want_map=True, want_pred=True)
+                det["prob_heatmap_nms"] = r["nms"]
+                det["pred_pts"] = r["pred"]
+            else:
+                det["pred_pts"] = torch.ge(prob, dh["det_thresh"]).to(torch.int32)
+            out = {"detector_output": det}
+            if hasattr(self, "descriptor_head"):
+                raw = ctx.descriptor_head_forward(B, H, W, self.mode)
+                d = {"desc_raw": raw}
+                if self.config.get("dense_desc", True):
+                    d["desc"] = ctx.dense_descriptors(raw, self.descriptor_head.config["grid_size"])
+                out["descriptor_output"] = d
+        return out
+
+    @torch.no_grad()
+    def prob_heatmap(self, images, mask=None, out=None):
+        """images (B,H,W) fp32 CUDA -> prob_heatmap (B,H,W), optionally multiplied by a u8 mask (export.py:69-70).
+        Skips everything ExportDetections.step discards (logits copy, in-model NMS)."""
+        ctx = self.native()
+        B, H, W = images.shape
+        with torch.cuda.device(images.device):
+            ctx.encoder_forward(images, self.mode)
+            prob, _ = ctx.detector_head_forward(B, H, W, self.mode, mask=mask, want_logits=False, out=out)
+        return prob

@@ -1,0 +1,332 @@
+"""GPU parity tests proper: every call goes through the C-ABI library (ctypes) and is compared with the oracle on
+the same seeded inputs and with the golden vectors produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star): fp32 heatmaps / descriptors 1e-4 relative (max|a-b| / max|b|) in strict
+mode; NMS / top-k / thresholds bit-exact given the same heatmap; keypoint sets >= 99 % within 1 px end to end."""
+import copy
+import os
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import HA_CFG, MP_MODEL, SP_MODEL, keypoint_agreement, rel_err, smooth_image
+from oracle import spn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+STRICT = 1e-4
+
+
+@pytest.fixture(scope="module")
+def P():
+    import superpoint_nerf_pytorch_b200 as pkg
+    assert pkg.library_path().exists(), "libspn_b200.so missing: the GPU tests never fall back to PyTorch"
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def ctx(P):
+    return P.get_context("cuda:0")
+
+
+def make_model(cfg, sd, precision="fp32"):
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    c = copy.deepcopy(cfg)
+    c["precision"] = precision
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    return m
+
+
+# ------------------------------------------------------------------------------------------------ NMS
+def test_box_nms_golden_bit_exact(ctx, golden):
+    from superpoint_nerf_pytorch_b200.models.model_utils.sp_utils import box_nms
+    g = golden("nms_cases.npz")
+    for i in range(int(g["n"])):
+        p, par, want = g[f"c{i}_prob"], g[f"c{i}_par"], g[f"c{i}_out"]
+        got = box_nms(torch.from_numpy(p).cuda(), par[0], par[1], par[2], int(par[3])).cpu().numpy()
+        assert np.array_equal(got, want), f"golden nms case {i}"
+
+
+@pytest.mark.parametrize("shape,size,min_prob,topk,kind", [
+    ((240, 320), 4, 0.015, 0, "flat"), ((480, 640), 4, 0.001, 1000, "flat"), ((120, 160), 4, 0.001, 0, "flat"),
+    ((240, 320), 8, 0.1, 300, "uniform"), ((96, 128), 3, 0.2, 0, "ties"), ((64, 512), 4, 0.0, 0, "ramp"),
+    ((8, 8), 4, 0.5, 3, "uniform"), ((240, 320), 4, 2.0, 5, "uniform")])
+def test_box_nms_vs_oracle(ctx, shape, size, min_prob, topk, kind):
+    rng = np.random.RandomState(hash((shape, size, kind)) % 2**31)
+    h, w = shape
+    if kind == "flat":       # random-init heatmap: ~1/65 everywhere, nearly every pixel is a candidate
+        p = (1 / 65 + 0.0005 * rng.randn(h, w)).astype(np.float32)
+    elif kind == "uniform":
+        p = rng.rand(h, w).astype(np.float32)
+    elif kind == "ties":
+        p = (np.round(rng.rand(h, w) * 6) / 6).astype(np.float32)
+    else:                    # monotone ramp: worst case for the number of fixed-point rounds
+        p = (np.arange(h * w, dtype=np.float32).reshape(h, w)[:, ::-1] / (h * w)).copy()
+    want = O.box_nms_c(p, size, 0.1, min_prob, topk).numpy()
+    pt = torch.from_numpy(p).cuda().unsqueeze(0)
+    r = ctx.box_nms(pt, size, 0.1, min_prob, topk, det_thresh=min_prob, want_map=True, want_pred=True, max_kp=h * w)
+    assert np.array_equal(r["nms"][0].cpu().numpy(), want)
+    assert np.array_equal(r["pred"][0].cpu().numpy(), (want >= min_prob).astype(np.int32))
+    n = int(r["kp_count"][0])
+    kp_want = np.argwhere(want >= min_prob)
+    assert n == len(kp_want)
+    assert np.array_equal(r["kp"][0, :n].cpu().numpy(), kp_want)
+
+
+def test_box_nms_batched_and_empty(ctx):
+    rng = np.random.RandomState(0)
+    p = rng.rand(5, 48, 64).astype(np.float32)
+    p[2] = 0.0  # empty image
+    r = ctx.box_nms(torch.from_numpy(p).cuda(), 4, 0.1, 0.3, 0, det_thresh=0.3, max_kp=64)
+    for i in range(5):
+        want = O.box_nms_c(p[i], 4, 0.1, 0.3, 0).numpy()
+        assert np.array_equal(r["nms"][i].cpu().numpy(), want)
+        assert int(r["kp_count"][i]) == int((want >= 0.3).sum())  # true count even when it exceeds max_kp
+    assert int(r["kp_count"][2]) == 0
+
+
+# ------------------------------------------------------------------------------------------------ forward
+@pytest.mark.parametrize("tag,cfg", [("magicpoint", MP_MODEL), ("superpoint", SP_MODEL)])
+def test_forward_strict_vs_golden(P, golden, tag, cfg):
+    g = golden(f"forward_{tag}.npz")
+    sd = O.make_state_dict(cfg["model_name"], seed=int(g["seed"]), logit_gain=float(g["gain"]))
+    m = make_model(cfg, sd)
+    out = m(torch.from_numpy(g["x"]).cuda())
+    det = out["detector_output"]
+    assert det["logits"].shape == g["logits"].shape and det["pred_pts"].dtype == torch.int32
+    assert rel_err(det["logits"].cpu().numpy(), g["logits"]) < STRICT
+    assert rel_err(det["prob_heatmap"].cpu().numpy(), g["prob_heatmap"]) < STRICT
+    # NMS is bit-exact when given the reference's heatmap
+    ctx = m.native()
+    dh = cfg["detector_head"]
+    r = ctx.box_nms(torch.from_numpy(g["prob_heatmap"]).cuda(), dh["nms"], 0.1, dh["det_thresh"], dh["top_k"],
+                    det_thresh=dh["det_thresh"], want_pred=True)
+    assert np.array_equal(r["nms"].cpu().numpy(), g["prob_heatmap_nms"])
+    assert np.array_equal(r["pred"].cpu().numpy(), g["pred_pts"])
+    # and the model's own NMS output agrees as a keypoint set
+    a, b = keypoint_agreement(np.argwhere(det["pred_pts"][0].cpu().numpy() > 0), np.argwhere(g["pred_pts"][0] > 0))
+    assert a >= 0.99 and b >= 0.99
+    if tag == "superpoint":
+        d = out["descriptor_output"]
+        assert rel_err(d["desc_raw"].cpu().numpy(), g["desc_raw"]) < STRICT
+        assert tuple(d["desc"].shape) == tuple(g["desc_shape"])
+        pts = g["desc_pts"]
+        dense = d["desc"][0].cpu().numpy()[:, pts[:, 0], pts[:, 1]].T
+        assert rel_err(dense, g["desc_at_pts"]) < STRICT
+        kp = torch.from_numpy(pts.astype(np.int32)).cuda().unsqueeze(0).contiguous()
+        cnt = torch.tensor([len(pts)], dtype=torch.int32, device="cuda")
+        sparse = ctx.sample_descriptors(torch.from_numpy(g["desc_raw"]).cuda(), 8, kp, cnt)[0].cpu().numpy()
+        assert rel_err(sparse, g["desc_at_pts"]) < STRICT
+        assert np.abs(np.linalg.norm(sparse, axis=1) - 1).max() < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 240, 320), (3, 120, 160), (1, 64, 72)])
+def test_forward_strict_vs_oracle_full_size(P, shape):
+    B, H, W = shape
+    sd = O.make_state_dict("superpoint", seed=21, logit_gain=6.0)
+    m = make_model(SP_MODEL, sd)
+    x = torch.from_numpy(np.stack([smooth_image(H, W, 40 + i) for i in range(B)])[:, None])
+    want = O.model_forward(sd, x, SP_MODEL, dense_desc=False)
+    got = m(x.cuda())
+    assert rel_err(got["detector_output"]["logits"].cpu().numpy(), want["detector_output"]["logits"].numpy()) < STRICT
+    assert rel_err(got["detector_output"]["prob_heatmap"].cpu().numpy(), want["detector_output"]["prob_heatmap"].numpy()) < STRICT
+    assert rel_err(got["descriptor_output"]["desc_raw"].cpu().numpy(), want["descriptor_output"]["desc_raw"].numpy()) < STRICT
+    # size-independent property: every 8x8 cell of the heatmap plus its dustbin sums to 1
+    lg = got["detector_output"]["logits"]
+    dust = torch.softmax(lg, 1)[:, -1]
+    cells = got["detector_output"]["prob_heatmap"].view(B, H // 8, 8, W // 8, 8).sum((2, 4))
+    assert float((cells + dust - 1).abs().max()) < 1e-5
+
+
+def test_forward_random_init_config1(P):
+    """BASELINE config 1 shape: MagicPoint 32x1x120x160, default-style init (flat ~1/65 heatmap), NMS radius 4."""
+    cfg = copy.deepcopy(MP_MODEL)
+    cfg["detector_head"]["det_thresh"] = 0.001
+    sd = O.make_state_dict("magicpoint", seed=0, logit_gain=1.0, randomize_bn=False)
+    m = make_model(cfg, sd)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((32, 1, 120, 160), generator=g)
+    got = m(x.cuda())["detector_output"]
+    want = O.model_forward(sd, x[:2], cfg, nms_fn=O.box_nms_c)["detector_output"]
+    assert rel_err(got["prob_heatmap"][:2].cpu().numpy(), want["prob_heatmap"].numpy()) < STRICT
+    # NMS bit-exact on our own heatmap vs the oracle's greedy NMS on the same heatmap
+    ours = got["prob_heatmap"].cpu().numpy()
+    for i in (0, 31):
+        ref = O.box_nms_c(ours[i], 4, 0.1, 0.001, 0).numpy()
+        assert np.array_equal(got["prob_heatmap_nms"][i].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ warp / masks
+def test_warp_batch_vs_golden_step(ctx, golden):
+    g = golden("ha_step.npz")
+    img = torch.from_numpy(g["image"][0]).cuda()            # (1,H,W)
+    h = torch.from_numpy(g["H"]).cuda().view(1, 3, 3, 3).contiguous()
+    hinv = ctx.invert3x3(h)
+    assert rel_err(hinv.cpu().numpy()[0], torch.inverse(torch.from_numpy(g["H"])).numpy()) < 1e-5
+    warped, mask = ctx.warp_batch(img, hinv, 3)
+    assert np.array_equal(warped[0].cpu().numpy(), g["image"][0, 0]) and bool((mask[0] == 1).all())
+    for i in range(3):
+        w = warped[1 + i].cpu().numpy()
+        assert np.abs(w - g[f"warped{i}"]).max() < 2e-4          # bilinear values (image in [0,1])
+        mm = mask[1 + i].cpu().numpy().astype(np.int32)
+        assert (mm != g[f"mask{i}"]).sum() <= 2, "eroded validity mask differs beyond boundary rounding"
+
+
+def test_ha_aggregate_vs_golden_step(ctx, golden):
+    g = golden("ha_step.npz")
+    H, W = 120, 160
+    h = torch.from_numpy(g["H"]).cuda().view(1, 3, 3, 3).contiguous()
+    img = torch.from_numpy(g["image"][0]).cuda()
+    warped, mask = ctx.warp_batch(img, ctx.invert3x3(h), 3)
+    probs = (0.25 + 0.5 * warped) * mask                        # the golden step's fake model, times the mask
+    probs[0] = 0.0                                              # golden step started from zeros (export.py:76)
+    agg = ctx.ha_aggregate(probs.view(1, 4, H, W).contiguous(), h, 3, "sum")[0].cpu().numpy()
+    want_sum = sum(g[f"proj{i}"] for i in range(3))
+    want_cnt = 1 + sum(g[f"count{i}"] for i in range(3))
+    want = want_sum / want_cnt
+    bad = np.abs(agg - want) > 1e-4 * np.abs(want).max()
+    assert bad.mean() < 2e-4, f"{bad.sum()} pixels off"         # only mask-boundary pixels may differ
+    mx = ctx.ha_aggregate(probs.view(1, 4, H, W).contiguous(), h, 3, "max")[0].cpu().numpy()
+    want_mx = np.max(np.stack([g[f"proj{i}"] for i in range(3)]), 0)
+    assert (np.abs(mx - want_mx) > 1e-4).mean() < 2e-4
+
+
+def test_warp_identity_and_shift_properties(ctx):
+    """Size-independent properties at BASELINE size: identity is exact; an integer shift is an exact shift."""
+    H, W = 240, 320
+    img = torch.from_numpy(smooth_image(H, W, 3)).cuda().unsqueeze(0)
+    eye = torch.eye(3, device="cuda")
+    shift = torch.tensor([[1.0, 0, 5], [0, 1, -3], [0, 0, 1]], device="cuda")   # H: p -> p + (5,-3)
+    h = torch.stack([eye, shift]).view(1, 2, 3, 3).contiguous()
+    warped, mask = ctx.warp_batch(img, ctx.invert3x3(h), 3)
+    assert torch.equal(warped[1], img[0]) and bool((mask[1] == 1).all())
+    w2 = warped[2].cpu().numpy()
+    src = img[0].cpu().numpy()
+    assert np.array_equal(w2[:-3, 5:], src[3:, :-5])           # out(p) = src(p - (5,-3))
+    assert np.all(w2[:, :5] == 0) and np.all(w2[-3:, :] == 0)
+    probs = torch.stack([img[0], warped[1] * mask[1]]).view(1, 2, H, W).contiguous()
+    agg = ctx.ha_aggregate(probs, eye.view(1, 1, 3, 3).contiguous(), 3, "sum")
+    assert float((agg[0] - img[0]).abs().max()) < 1e-7           # mean of two identical maps
+
+
+# ------------------------------------------------------------------------------------------------ sampler
+def test_device_sampler_statistics(ctx):
+    n = 4000
+    h, hinv = ctx.sample_homographies(HA_CFG["params"], seed=5, first_index=0, count=n, H=240, W=320)
+    h, hinv = h.cpu().double(), hinv.cpu().double()
+    eye = torch.eye(3, dtype=torch.float64)
+    assert float((torch.bmm(h, hinv) - eye).abs().max()) < 1e-3
+    np.random.seed(77)
+    ref = torch.cat([O.sample_homography((240, 320), **HA_CFG["params"]) for _ in range(n)]).double()
+    # compare distributions of a few functionals of the matrices (not the RNG stream)
+    def feats(m):
+        m = m / m[:, 2:3, 2:3]
+        ang = torch.atan2(m[:, 1, 0], m[:, 0, 0])
+        sc = torch.sqrt(m[:, 0, 0] ** 2 + m[:, 1, 0] ** 2)
+        c = m @ torch.tensor([160.0, 120.0, 1.0], dtype=torch.float64)
+        return torch.stack([ang, sc, c[:, 0] / c[:, 2], c[:, 1] / c[:, 2], m[:, 2, 0] * 1e3, m[:, 2, 1] * 1e3], 1).numpy()
+    a, b = feats(h), feats(ref)
+    for k in range(a.shape[1]):
+        qa = np.quantile(a[:, k], [0.1, 0.25, 0.5, 0.75, 0.9])
+        qb = np.quantile(b[:, k], [0.1, 0.25, 0.5, 0.75, 0.9])
+        spread = max(b[:, k].std(), 1e-9)
+        assert np.abs(qa - qb).max() < 0.12 * spread + 1e-6, (k, qa, qb)
+    # same (seed, index) -> same matrix regardless of batch split
+    h2, _ = ctx.sample_homographies(HA_CFG["params"], seed=5, first_index=100, count=10, H=240, W=320)
+    assert torch.equal(h2.cpu().double(), h[100:110])
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def test_ha_export_end_to_end_vs_golden(P, golden, tmp_path, monkeypatch):
+    from superpoint_nerf_pytorch_b200 import settings
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import ExportDetections, HomographyAdaptation
+    g = golden("ha_export.npz")
+    sd = O.make_state_dict("magicpoint", seed=int(g["seed"]), logit_gain=float(g["gain"]))
+    m = make_model(MP_MODEL, sd)
+    cfg = {"data": {"experiment_name": "gpu_golden"}, "homography_adaptation": copy.deepcopy(HA_CFG), "model": copy.deepcopy(MP_MODEL)}
+    eng = HomographyAdaptation(cfg, m, "cuda")
+    img = torch.from_numpy(g["image"]).cuda()
+    heat, _ = eng.heatmaps(img, homographies=torch.from_numpy(g["H"]).view(1, 7, 3, 3))
+    agg = heat[0].cpu().numpy()
+    bad = np.abs(agg - g["agg"]) > STRICT * np.abs(g["agg"]).max()
+    assert bad.mean() < 5e-4, f"{bad.sum()} pixels of the aggregated heatmap off by more than 1e-4 relative"
+    kp = eng.keypoints(heat)[0]
+    assert kp.dtype == np.int64 and kp.shape[1] == 2
+    a, b = keypoint_agreement(kp, g["keypoints"])
+    assert a >= 0.99 and b >= 0.99, (a, b, len(kp), len(g["keypoints"]))
+    # NMS + threshold + nonzero on the REFERENCE's aggregated heatmap is bit-exact
+    kp_ref = eng.keypoints(torch.from_numpy(g["agg"]).cuda().unsqueeze(0))[0]
+    assert np.array_equal(kp_ref, g["keypoints"])
+    # the task class: numpy sampler + same numpy seed -> same homographies as the reference -> same file
+    monkeypatch.setattr(settings, "EXPER_PATH", str(tmp_path))
+    cfg["homography_adaptation"]["sampler"] = "numpy"
+    np.random.seed(int(g["np_seed"]))
+    loader = [{"raw": {"image": torch.from_numpy(g["image"])}, "name": ["img0"]}]
+    ExportDetections(cfg, m, loader, "training", True, "cuda")
+    f = Path(tmp_path, "outputs", "gpu_golden", "training", "img0.npy")
+    saved = np.load(f)
+    assert saved.dtype == np.int64 and saved.ndim == 2 and saved.shape[1] == 2
+    a, b = keypoint_agreement(saved, g["keypoints"])
+    assert a >= 0.99 and b >= 0.99
+    lin = saved[:, 0] * 160 + saved[:, 1]
+    assert np.all(np.diff(lin) > 0)                      # row-major order like torch.nonzero
+    mtime = f.stat().st_mtime_ns
+    ExportDetections(cfg, m, loader, "training", True, "cuda")   # resume: existing file is skipped
+    assert f.stat().st_mtime_ns == mtime
+
+
+def test_ha_full_size_vs_oracle(P):
+    """BASELINE config 2 shape (240x320) with fewer homographies so the CPU oracle finishes in seconds."""
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import HomographyAdaptation
+    sd = O.make_state_dict("magicpoint", seed=5, logit_gain=10.0)
+    m = make_model(MP_MODEL, sd)
+    ha = copy.deepcopy(HA_CFG)
+    ha["num"] = 6
+    cfg = {"homography_adaptation": ha, "model": copy.deepcopy(MP_MODEL)}
+    img = torch.from_numpy(smooth_image(240, 320, 8))[None, None]
+    np.random.seed(2)
+    want = O.homography_adaptation(sd, img, cfg, nms_fn=O.box_nms_c)
+    eng = HomographyAdaptation(cfg, m, "cuda")
+    heat, _ = eng.heatmaps(img.cuda(), homographies=want["homographies"].view(1, 5, 3, 3))
+    agg = heat[0].cpu().numpy()
+    bad = np.abs(agg - want["mean_prob"].numpy()) > STRICT * float(want["mean_prob"].abs().max())
+    assert bad.mean() < 5e-4
+    a, b = keypoint_agreement(eng.keypoints(heat)[0], want["keypoints"])
+    assert a >= 0.99 and b >= 0.99
+    # two images per launch give the same result as one at a time (batching is transparent)
+    img2 = torch.from_numpy(smooth_image(240, 320, 9))[None, None]
+    both = torch.cat([img, img2]).cuda()
+    hs = torch.cat([want["homographies"].view(1, 5, 3, 3)] * 2)
+    heat2, _ = eng.heatmaps(both, homographies=hs)
+    assert torch.equal(heat2[0], heat[0])
+
+
+def test_hpatches_exports_layout(P, golden, tmp_path, monkeypatch):
+    from superpoint_nerf_pytorch_b200 import settings
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import Export_Hpatches_Descriptors, Export_Hpatches_Repeatability
+    g = golden("hpatches_export.npz")
+    sd = O.make_state_dict("superpoint", seed=4, logit_gain=12.0)
+    m = make_model(SP_MODEL, sd)
+    monkeypatch.setattr(settings, "EXPER_PATH", str(tmp_path))
+    loader = [{"image": torch.from_numpy(g["image"]), "warped_image": torch.from_numpy(g["warped_image"]),
+               "homography": torch.from_numpy(g["homography"]), "name": ["pair0"]}]
+    cfg = {"data": {"experiment_name": "hp"}, "model": copy.deepcopy(SP_MODEL)}
+    Export_Hpatches_Repeatability(cfg, m, loader, "cuda")
+    Export_Hpatches_Descriptors(cfg, m, loader, "cuda")
+    rep = np.load(Path(tmp_path, "repeatability", "hp", "pair0.npz"))
+    des = np.load(Path(tmp_path, "descriptors", "hp", "pair0.npz"))
+    for kind, f in (("rep", rep), ("des", des)):
+        keys = sorted(k.split("__")[1] for k in g.files if k.startswith(kind + "__") and k.endswith("__shape"))
+        assert sorted(f.files) == keys
+        for k in keys:
+            assert tuple(f[k].shape) == tuple(g[f"{kind}__{k}__shape"]), (kind, k)
+            assert str(f[k].dtype) == str(g[f"{kind}__{k}__dtype"]), (kind, k)
+    a, b = keypoint_agreement(np.argwhere(rep["prob"] > 0), np.argwhere(g["rep_prob"] > 0))
+    assert a >= 0.99 and b >= 0.99
+    pts = g["des_pts"]
+    assert rel_err(des["desc"][pts[:, 0], pts[:, 1]], g["des_desc_at_pts"]) < STRICT
+    assert rel_err(des["warped_desc"][pts[:, 0], pts[:, 1]], g["des_warped_desc_at_pts"]) < STRICT

@@ -1,0 +1,109 @@
+"""CPU: host-side mirror of the reference interface, and the C-ABI library (loads, exports every declared symbol,
+refuses to run without a GPU).  No compute calls here."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import HA_CFG, MP_MODEL, ROOT, SP_MODEL
+from oracle import spn_oracle as O
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("spn_build", ROOT / "superpoint-nerf-pytorch_b200" / "build.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "spn_b200.h").read_text()
+    return sorted(set(re.findall(r"SPN_API\s+[\w\s\*]+?\b(spn_\w+)\s*\(", text)))
+
+
+def test_cabi_exports_every_declared_symbol(built_lib):
+    names = declared_symbols()
+    assert len(names) >= 16, names
+    lib = ctypes.CDLL(str(built_lib))
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/spn_b200.h but not exported"
+    import superpoint_nerf_pytorch_b200._native as N
+    assert sorted(N.PROTOTYPES) == names, "ctypes prototypes and header are out of sync"
+    lib.spn_version.restype = ctypes.c_int
+    assert lib.spn_version() >= 100
+
+
+def test_no_silent_cpu_fallback(built_lib):
+    import superpoint_nerf_pytorch_b200 as P
+    from superpoint_nerf_pytorch_b200.models.model_utils.sp_utils import box_nms
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the GPU-less container")
+    with pytest.raises(P.NativeError):
+        P.Context()
+    with pytest.raises(P.NativeError):
+        box_nms(torch.zeros(8, 8), 4)
+    m = get_model(MP_MODEL, "cpu")
+    with pytest.raises(P.NativeError):
+        m(torch.zeros(1, 1, 16, 16))
+    lib = ctypes.CDLL(str(built_lib))
+    h = ctypes.c_void_p()
+    lib.spn_last_error.restype = ctypes.c_char_p
+    assert lib.spn_create(ctypes.byref(h), 0) != 0
+    assert b"no CPU fallback" in lib.spn_last_error() or b"CUDA" in lib.spn_last_error()
+
+
+def test_state_dict_is_reference_compatible():
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    for cfg in (MP_MODEL, SP_MODEL):
+        m = get_model(cfg, "cpu")
+        sd = O.make_state_dict(cfg["model_name"], seed=0)
+        assert set(sd) == set(m.state_dict())
+        assert all(sd[k].shape == v.shape for k, v in m.state_dict().items())
+        m.load_state_dict(sd)  # engine.py:108-117 style loading works
+    with pytest.raises(Exception):
+        get_model(MP_MODEL, "cpu").train()
+
+
+def test_host_sampler_bit_equal_to_reference(golden):
+    from superpoint_nerf_pytorch_b200.data.data_utils.homographic_augmentation import (Homographic_aug,
+                                                                                      perspective_from_corners,
+                                                                                      sample_corners)
+    g = golden("homographies.npz")
+    aug = Homographic_aug({"params": HA_CFG["params"], "valid_border_margin": 3}, "cpu")
+    for s in range(6):
+        np.random.seed(s)
+        got = torch.cat([aug.sample_homography((240, 320), **HA_CFG["params"]) for _ in range(3)]).numpy()
+        assert np.array_equal(got, g[f"s{s}"])
+    np.random.seed(100)
+    p2 = dict(HA_CFG["params"], allow_artifacts=False, patch_ratio=0.5, n_scales=5, n_angles=25, translation_overflow=0.0)
+    got = torch.cat([aug.sample_homography((120, 160), **p2) for _ in range(3)]).numpy()
+    assert np.array_equal(got, g["noartifact"])
+    import cv2
+    np.random.seed(1)
+    s, d = sample_corners(**HA_CFG["params"])
+    wh = np.array([[320, 240.0]])
+    M = cv2.getPerspectiveTransform(np.float32(s * wh), np.float32(d * wh))
+    assert np.abs(M - perspective_from_corners(s * wh, d * wh)).max() < 1e-5
+
+
+def test_move_to_device_and_get_model():
+    from superpoint_nerf_pytorch_b200.utils.train_utils import move_to_device
+    d = {"a": torch.zeros(2), "b": [torch.ones(1), "x"], "name": ["n"]}
+    out = move_to_device(d, "cpu")
+    assert out["name"] == ["n"] and out["b"][1] == "x" and torch.equal(out["a"], d["a"])
+
+
+def test_shard_plan():
+    from superpoint_nerf_pytorch_b200.utils.sharding import shard_indices
+    for n in (0, 1, 7, 10000):
+        for world in (1, 2, 4, 8):
+            parts = [shard_indices(n, r, world) for r in range(world)]
+            allidx = sorted(i for p in parts for i in p)
+            assert allidx == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
