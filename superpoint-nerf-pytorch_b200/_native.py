@@ -92,7 +92,12 @@ def _chk_dev(t: torch.Tensor, dtype, name):
     if t.dtype != dtype:
         raise NativeError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
-        raise NativeError(f"{name} must be contiguous")
+        raise NativeError(f"{name} must be contiguous (strides {t.stride()} for shape {tuple(t.shape)})")
+
+
+def _dense(t):
+    """Row-major dense view of a tensor (copies only if needed) - the C ABI takes dense arrays."""
+    return None if t is None else t.contiguous()
 
 
 class Context:
@@ -143,6 +148,7 @@ class Context:
 
     # ---- forward -------------------------------------------------------------------------------
     def encoder_forward(self, images: torch.Tensor, mode: int):
+        images = _dense(images)
         _chk_dev(images, torch.float32, "images")
         B, H, W = images.shape
         self._call("spn_encoder_forward", self.handle, _ptr(images), B, H, W, mode, _stream())
@@ -158,6 +164,7 @@ class Context:
             prob = out
         logits = torch.empty((B, 65, H // 8, W // 8), dtype=torch.float32, device=dev) if want_logits else None
         if mask is not None:
+            mask = _dense(mask)
             _chk_dev(mask, torch.uint8, "mask")
         self._call("spn_detector_head_forward", self.handle, B, H, W, mode, _ptr(mask), _ptr(logits), _ptr(prob), _stream())
         return prob, logits
@@ -168,6 +175,7 @@ class Context:
         return raw
 
     def dense_descriptors(self, raw: torch.Tensor, grid: int):
+        raw = _dense(raw)
         _chk_dev(raw, torch.float32, "desc_raw")
         B, Cc, Hc, Wc = raw.shape
         out = torch.empty((B, Cc, Hc * grid, Wc * grid), dtype=torch.float32, device=raw.device)
@@ -175,6 +183,7 @@ class Context:
         return out
 
     def sample_descriptors(self, raw, grid, kp, kp_count, interp="bicubic"):
+        raw, kp, kp_count = _dense(raw), _dense(kp), _dense(kp_count)
         _chk_dev(raw, torch.float32, "desc_raw")
         _chk_dev(kp, torch.int32, "kp")
         _chk_dev(kp_count, torch.int32, "kp_count")
@@ -188,6 +197,7 @@ class Context:
     def box_nms(self, prob, size, iou=0.1, min_prob=0.01, top_k=0, det_thresh=None, want_map=True, want_pred=False,
                 max_kp=0):
         """prob (B,H,W).  Returns dict(nms, pred, kp, kp_count) with the requested members."""
+        prob = _dense(prob)
         _chk_dev(prob, torch.float32, "prob")
         B, H, W = prob.shape
         dev = prob.device
@@ -204,6 +214,7 @@ class Context:
     # ---- homography adaptation -------------------------------------------------------------------
     def warp_batch(self, images, hinv, margin):
         """images (NI,H,W), hinv (NI,n_h,3,3) -> warped (NI*(n_h+1),H,W) fp32, mask u8 (same shape)."""
+        images, hinv = _dense(images), _dense(hinv)
         _chk_dev(images, torch.float32, "images")
         NI, H, W = images.shape
         n_h = 0 if hinv is None else hinv.shape[1]
@@ -217,6 +228,7 @@ class Context:
 
     def ha_aggregate(self, probs, h, margin, aggregation="sum"):
         """probs (NI,n_h+1,H,W) masked heatmaps, h (NI,n_h,3,3) -> (NI,H,W)."""
+        probs, h = _dense(probs), _dense(h)
         _chk_dev(probs, torch.float32, "probs")
         NI, n1, H, W = probs.shape
         n_h = n1 - 1
@@ -243,6 +255,7 @@ class Context:
         return h, hinv
 
     def invert3x3(self, m):
+        m = _dense(m)
         _chk_dev(m, torch.float32, "m")
         out = torch.empty_like(m)
         self._call("spn_invert3x3", self.handle, _ptr(m), m.numel() // 9, _ptr(out), _stream())
