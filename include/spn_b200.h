@@ -67,6 +67,13 @@ SPN_API int spn_pack_weights(spn_ctx* ctx, int layer, const float* h_w, const fl
                      const float* h_beta, const float* h_mean, const float* h_var, float eps, int cout, int cin,
                      int ksize, spn_stream stream);
 
+/* One VGG_Block.forward (VGG_Backbone.py:23-36): conv + folded BN (+ ReLU) (+ 2x2 max-pool), NCHW fp32 in and out.
+ * d_in [B][cin][H][W] -> d_out [B][cout][H or H/2][W or W/2].  In the tensor-core modes the activations are rounded
+ * to fp16/bf16 on the way in (this entry point exists for layer-level parity tests and for callers that want a
+ * single block; the fused forward keeps activations in the 16-bit C8 layout between layers). */
+SPN_API int spn_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_in, int B, int H, int W, int relu, int pool,
+                           float* d_out, spn_stream stream);
+
 /* VGG_BACKBONE.forward (VGG_Backbone.py:60-71): d_images [B][H][W] fp32 in [0,1] -> feature map kept inside ctx
  * (H, W multiples of 8). */
 SPN_API int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode, spn_stream stream);
@@ -132,6 +139,16 @@ SPN_API int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params* p
 
 /* 3x3 inverse, fp32, batched (export.py:49 torch.inverse). d_in/d_out [count][9]. */
 SPN_API int spn_invert3x3(spn_ctx* ctx, const float* d_in, int count, float* d_out, spn_stream stream);
+
+/* Per-kernel CUDA-event timing for bench.py's roofline leg.  Slots 0..11 = the convolution of layer SPN_L_*,
+ * then the bandwidth-bound kernels.  spn_profile_read synchronises, writes the accumulated milliseconds and launch
+ * counts per slot into HOST arrays of SPN_PROF_SLOTS entries and resets the counters. */
+enum {
+  SPN_PROF_WARP = 12, SPN_PROF_AGGREGATE = 13, SPN_PROF_NMS = 14, SPN_PROF_SOFTMAX = 15, SPN_PROF_DESC = 16,
+  SPN_PROF_PREP = 17, SPN_PROF_SAMPLER = 18, SPN_PROF_SLOTS = 24
+};
+SPN_API int spn_profile_enable(spn_ctx* ctx, int enable);
+SPN_API int spn_profile_read(spn_ctx* ctx, float* h_ms, int64_t* h_count);
 
 /* number of kernels launched through this context since creation (bench.py's gpu_launches) */
 SPN_API int64_t spn_launch_count(spn_ctx* ctx);

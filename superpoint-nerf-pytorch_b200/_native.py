@@ -41,6 +41,7 @@ PROTOTYPES = {
     "spn_create": (_i, [C.POINTER(_vp), _i]),
     "spn_destroy": (_i, [_vp]),
     "spn_pack_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
+    "spn_conv_layer": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "spn_encoder_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "spn_detector_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "spn_descriptor_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
@@ -52,6 +53,8 @@ PROTOTYPES = {
     "spn_sample_homographies": (_i, [_vp, C.POINTER(HomographyParams), C.c_uint64, C.c_uint64, _i, _i, _i, _vp, _vp, _vp]),
     "spn_invert3x3": (_i, [_vp, _vp, _i, _vp, _vp]),
     "spn_launch_count": (C.c_int64, [_vp]),
+    "spn_profile_enable": (_i, [_vp, _i]),
+    "spn_profile_read": (_i, [_vp, _vp, _vp]),
 }
 
 _lib = None
@@ -133,6 +136,20 @@ class Context:
     def launches(self) -> int:
         return int(self.lib.spn_launch_count(self.handle))
 
+    PROF_SLOTS = 24
+    PROF_NAMES = {i: n for i, n in enumerate(LAYER_PREFIXES)} | {12: "warp_batch", 13: "ha_aggregate", 14: "box_nms",
+                                                                 15: "softmax_d2s", 16: "dense_desc", 17: "prep", 18: "sampler"}
+
+    def profile_enable(self, on: bool):
+        self._call("spn_profile_enable", self.handle, 1 if on else 0)
+
+    def profile_read(self):
+        """-> {kernel name: (total ms, launches)} since the last read (CUDA events recorded inside the library)."""
+        ms = (C.c_float * self.PROF_SLOTS)()
+        cnt = (C.c_int64 * self.PROF_SLOTS)()
+        self._call("spn_profile_read", self.handle, C.cast(ms, C.c_void_p), C.cast(cnt, C.c_void_p))
+        return {self.PROF_NAMES.get(i, f"slot{i}"): (float(ms[i]), int(cnt[i])) for i in range(self.PROF_SLOTS) if cnt[i]}
+
     # ---- weights -------------------------------------------------------------------------------
     def load_state_dict(self, sd: dict, eps: float = 1e-5):
         """Fold BN and upload every VGG_Block present in a reference-format state dict (engine.py:108-117)."""
@@ -145,6 +162,15 @@ class Context:
             cout, cin, k, _ = w.shape
             self._call("spn_pack_weights", self.handle, lid, _ptr(w), _ptr(b), _ptr(g), _ptr(be), _ptr(mu), _ptr(var),
                        C.c_float(eps), cout, cin, k, _stream())
+
+    def conv_layer(self, layer: int, x: torch.Tensor, mode: int, relu=True, pool=False, cout=None):
+        """One VGG_Block (conv + folded BN [+ ReLU] [+ 2x2 max-pool]) on NCHW fp32 tensors."""
+        x = _dense(x)
+        _chk_dev(x, torch.float32, "x")
+        B, _, H, W = x.shape
+        out = torch.empty((B, cout, H // 2 if pool else H, W // 2 if pool else W), dtype=torch.float32, device=x.device)
+        self._call("spn_conv_layer", self.handle, layer, mode, _ptr(x), B, H, W, int(relu), int(pool), _ptr(out), _stream())
+        return out
 
     # ---- forward -------------------------------------------------------------------------------
     def encoder_forward(self, images: torch.Tensor, mode: int):

@@ -177,6 +177,7 @@ int spn_conv_fp32(spn_ctx* ctx, int layer, const float* in, float* out, int B, i
   SPN_REQUIRE(!pool || L.ks == 3, "pooling only fused into 3x3 layers");
   const int tiles_x = spn_cdiv(W, kTW), tiles_y = spn_cdiv(H, kTH);
   dim3 grid(tiles_x * tiles_y, L.cout_pad / kCoTile, B), block(256);
+  SpnProfScope prof(ctx, layer, s);
   if (L.ks == 3) {
     if (pool)
       conv_fp32_kernel<3, true><<<grid, block, 0, s>>>(in, L.w32, L.bias, out, L.cin, L.cout, L.cout_pad, H, W, tiles_x, relu);
@@ -192,6 +193,7 @@ int spn_conv_fp32(spn_ctx* ctx, int layer, const float* in, float* out, int B, i
 int spn_softmax_d2s(spn_ctx* ctx, const float* logits, int B, int Hc, int Wc, const uint8_t* mask, float* prob,
                     cudaStream_t s) {
   const int n = B * Hc * Wc;
+  SpnProfScope prof(ctx, SPN_PROF_SOFTMAX, s);
   softmax_d2s_kernel<<<spn_cdiv(n, 128), 128, 0, s>>>(logits, mask, prob, B, Hc, Wc);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;

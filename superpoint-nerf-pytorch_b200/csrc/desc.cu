@@ -128,6 +128,7 @@ extern "C" int spn_dense_descriptors(spn_ctx* ctx, const float* d_desc_raw, int 
   SPN_REQUIRE(smem <= 200 * 1024, "spn_dense_descriptors: too many channels");
   if (smem > 48 * 1024) SPN_CUDA(cudaFuncSetAttribute(dense_desc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 g(spn_cdiv(W, 32), H, B);
+  SpnProfScope prof(ctx, SPN_PROF_DESC, (cudaStream_t)stream);
   dense_desc_kernel<<<g, 256, smem, (cudaStream_t)stream>>>(d_desc_raw, C, Hc, Wc, grid, d_desc);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;

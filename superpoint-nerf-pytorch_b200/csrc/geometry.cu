@@ -348,6 +348,7 @@ extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images,
   const ErodeK ek = make_ellipse(margin);
   const int tiles_x = spn_cdiv(W, kTileW), tiles_y = spn_cdiv(H, kTileH);
   dim3 grid(tiles_x * tiles_y, n_images * (n_h + 1));
+  SpnProfScope prof(ctx, SPN_PROF_WARP, (cudaStream_t)stream);
   warp_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_images, d_hinv, n_h, H, W, tiles_x, ek, d_warped, d_mask);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
@@ -364,6 +365,7 @@ extern "C" int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float*
   const ErodeK ek = make_ellipse(margin);
   const int tiles_x = spn_cdiv(W, kTileW), tiles_y = spn_cdiv(H, kTileH);
   dim3 grid(tiles_x * tiles_y, n_images);
+  SpnProfScope prof(ctx, SPN_PROF_AGGREGATE, (cudaStream_t)stream);
   ha_aggregate_kernel<<<grid, 256, n_h * 9 * sizeof(float), (cudaStream_t)stream>>>(d_probs, d_h, n_h, H, W, tiles_x, ek,
                                                                                      aggregation, d_out);
   SPN_CHECK_LAUNCH(ctx);
@@ -378,6 +380,7 @@ extern "C" int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params
   SPN_REQUIRE(params->n_scales >= 1 && params->n_scales <= 31 && params->n_angles >= 1 && params->n_angles <= 63,
               "spn_sample_homographies: n_scales must be in [1,31], n_angles in [1,63]");
   if (count == 0) return SPN_OK;
+  SpnProfScope prof(ctx, SPN_PROF_SAMPLER, (cudaStream_t)stream);
   sample_homographies_kernel<<<spn_cdiv(count, 64), 64, 0, (cudaStream_t)stream>>>(*params, seed, first_index, count, H,
                                                                                     W, d_h, d_hinv);
   SPN_CHECK_LAUNCH(ctx);

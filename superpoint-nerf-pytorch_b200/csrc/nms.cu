@@ -214,6 +214,7 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
   cudaStream_t s = (cudaStream_t)stream;
   int rc = spn_ensure_aux(ctx, (size_t)B * H * W, s);
   if (rc) return rc;
+  SpnProfScope prof(ctx, SPN_PROF_NMS, s);
   box_nms_kernel<<<B, kThreads, 0, s>>>(d_prob, (uint8_t*)ctx->aux, foot, H, W, min_prob, top_k, det_thresh, d_nms,
                                         d_pred, d_kp, d_kp_count, max_kp);
   SPN_CHECK_LAUNCH(ctx);

@@ -83,6 +83,27 @@ extern "C" int spn_destroy(spn_ctx* ctx) {
 
 extern "C" int64_t spn_launch_count(spn_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+extern "C" int spn_profile_enable(spn_ctx* ctx, int enable) {
+  SPN_REQUIRE(ctx, "spn_profile_enable: null ctx");
+  ctx->prof_on = enable != 0;
+  return SPN_OK;
+}
+
+extern "C" int spn_profile_read(spn_ctx* ctx, float* h_ms, int64_t* h_count) {
+  SPN_REQUIRE(ctx && h_ms && h_count, "spn_profile_read: null pointer");
+  for (int i = 0; i < SPN_PROF_SLOTS; ++i) { h_ms[i] = 0.f; h_count[i] = 0; }
+  for (auto& r : ctx->prof) {
+    float ms = 0.f;
+    SPN_CUDA(cudaEventSynchronize(r.b));
+    SPN_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (r.slot >= 0 && r.slot < SPN_PROF_SLOTS) { h_ms[r.slot] += ms; h_count[r.slot] += 1; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  ctx->prof.clear();
+  return SPN_OK;
+}
+
 extern "C" int spn_pack_weights(spn_ctx* ctx, int layer, const float* h_w, const float* h_b, const float* h_gamma,
                                 const float* h_beta, const float* h_mean, const float* h_var, float eps, int cout,
                                 int cin, int ksize, spn_stream stream) {
@@ -207,8 +228,8 @@ extern "C" int spn_detector_head_forward(spn_ctx* ctx, int B, int H, int W, int 
     if ((rc = spn_conv_fp32(ctx, SPN_L_CONVPA, (const float*)ctx->feat, A, B, Hc, Wc, true, false, s))) return rc;
     if ((rc = spn_conv_fp32(ctx, SPN_L_CONVPB, A, logits, B, Hc, Wc, false, false, s))) return rc;
   } else {
+    if (!logits) logits = spn_tc_logits_scratch(ctx, B, H, W);
     if ((rc = spn_tc_detector_head(ctx, B, H, W, mode, logits, s))) return rc;
-    if (!logits) return SPN_OK;  // unreachable: tc path always materialises logits (see conv_tc.cu)
   }
   return spn_softmax_d2s(ctx, logits, B, Hc, Wc, d_mask, d_prob, s);
 }
@@ -231,4 +252,18 @@ extern "C" int spn_descriptor_head_forward(spn_ctx* ctx, int B, int H, int W, in
     return spn_conv_fp32(ctx, SPN_L_CONVDB, A, d_desc_raw, B, Hc, Wc, false, false, s);
   }
   return spn_tc_descriptor_head(ctx, B, H, W, mode, d_desc_raw, s);
+}
+
+extern "C" int spn_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_in, int B, int H, int W, int relu,
+                              int pool, float* d_out, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_in && d_out, "spn_conv_layer: null pointer");
+  SPN_REQUIRE(layer >= 0 && layer < SPN_NUM_LAYERS && ctx->layers[layer].w32, "spn_conv_layer: layer %d has no weights", layer);
+  SPN_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "spn_conv_layer: bad shape");
+  SPN_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0 && ctx->layers[layer].ks == 3), "spn_conv_layer: pooling needs even H, W and a 3x3 layer");
+  cudaStream_t s = (cudaStream_t)stream;
+  SPN_CUDA(cudaSetDevice(ctx->device));
+  ctx->feat_mode = -1;  // the workspace is reused
+  if (mode == SPN_MODE_FP32 || ctx->layers[layer].cin % 64 != 0) return spn_conv_fp32(ctx, layer, d_in, d_out, B, H, W, relu != 0, pool != 0, s);
+  SPN_REQUIRE(mode == SPN_MODE_F16 || mode == SPN_MODE_BF16, "spn_conv_layer: unknown mode %d", mode);
+  return spn_tc_conv_layer(ctx, layer, mode, d_in, B, H, W, relu != 0, pool != 0, d_out, s);
 }

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/spn_b200.h"
 
 struct SpnLayer {
@@ -16,7 +18,14 @@ struct SpnLayer {
   void* w16[2] = {nullptr, nullptr};  // tcgen05 operand-B images (fp16, bf16), see conv_tc.cu
 };
 
+struct SpnProfRec {
+  int slot;
+  cudaEvent_t a, b;
+};
+
 struct spn_ctx {
+  bool prof_on = false;
+  std::vector<SpnProfRec> prof;
   int device = 0;
   int sm_count = 148;
   SpnLayer layers[SPN_NUM_LAYERS];
@@ -60,6 +69,25 @@ void spn_set_error(const char* fmt, ...);
     }                                                                                          \
   } while (0)
 
+// CUDA-event bracket around a group of launches, active only after spn_profile_enable(ctx, 1)
+struct SpnProfScope {
+  spn_ctx* c;
+  cudaStream_t s;
+  SpnProfRec r;
+  bool on;
+  SpnProfScope(spn_ctx* ctx, int slot, cudaStream_t st) : c(ctx), s(st), on(ctx->prof_on) {
+    if (!on) return;
+    r.slot = slot;
+    on = cudaEventCreate(&r.a) == cudaSuccess && cudaEventCreate(&r.b) == cudaSuccess;
+    if (on) cudaEventRecord(r.a, s);
+  }
+  ~SpnProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, s);
+    c->prof.push_back(r);
+  }
+};
+
 int spn_ensure_ws(spn_ctx* ctx, size_t bytes, cudaStream_t s);
 int spn_ensure_aux(spn_ctx* ctx, size_t bytes, cudaStream_t s);
 
@@ -75,5 +103,8 @@ int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int
 int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_logits, cudaStream_t s);
 int spn_tc_descriptor_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw, cudaStream_t s);
 void spn_tc_destroy(spn_ctx* ctx);
+float* spn_tc_logits_scratch(spn_ctx* ctx, int B, int H, int W);
+int spn_tc_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_in, int B, int H, int W, bool relu, bool pool,
+                      float* d_out, cudaStream_t s);
 
 static inline int spn_cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -1,0 +1,92 @@
+"""GPU parity of the tcgen05 (fp16 / bf16 operand, fp32 accumulate) convolution path against the fp32 oracle.
+
+Tolerance: 5e-3 relative (max|a-b| / max|b|) for fp16 operands - the north_star's stated gate for reduced-precision
+convolutions; bf16 operands (8 mantissa bits) are held to 3e-2 and are not the default fast mode."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import HA_CFG, MP_MODEL, SP_MODEL, keypoint_agreement, rel_err, smooth_image
+from oracle import spn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FAST = 5e-3
+LAYER_ID = {n: i for i, (n, *_r) in enumerate(O.layer_table(superpoint=True))}
+
+
+@pytest.fixture(scope="module")
+def sp_model():
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    sd = O.make_state_dict("superpoint", seed=21, logit_gain=6.0)
+    c = copy.deepcopy(SP_MODEL)
+    c["precision"] = "f16"
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    return m, sd
+
+
+@pytest.mark.parametrize("name,shape,mode", [
+    ("backbone.block_2", (2, 64, 48, 40), 1), ("backbone.block_3", (1, 64, 32, 24), 1),
+    ("backbone.block_5", (2, 64, 30, 40), 1), ("backbone.block_6", (1, 128, 60, 80), 1),
+    ("backbone.block_8", (3, 128, 30, 40), 1), ("detector_head.convPa", (2, 128, 30, 40), 1),
+    ("detector_head.convPb", (2, 256, 30, 40), 1), ("descriptor_head.convDb", (1, 256, 15, 20), 1),
+    ("backbone.block_2", (1, 64, 240, 320), 1), ("backbone.block_4", (1, 64, 16, 8), 2),
+    ("backbone.block_7", (1, 128, 5, 6), 1)])
+def test_tc_conv_layer_vs_fp32(sp_model, name, shape, mode):
+    m, sd = sp_model
+    ctx = m.native()
+    lid = LAYER_ID[name]
+    _n, cin, cout, k, relu, pool = O.layer_table(superpoint=True)[lid]
+    if shape[2] % 2 or shape[3] % 2:
+        pool = False
+    rng = np.random.RandomState(lid)
+    x = torch.from_numpy(np.maximum(rng.randn(*shape), 0).astype(np.float32))
+    xr = x.half().float() if mode == 1 else x.bfloat16().float()       # what the 16-bit path sees
+    want = O.vgg_block(sd, name, xr, k, relu, pool).numpy()
+    got = ctx.conv_layer(lid, x.cuda(), mode, relu=relu, pool=pool, cout=cout).cpu().numpy()
+    assert got.shape == want.shape
+    err = rel_err(got, want)
+    assert err < (FAST if mode == 1 else 3e-2), f"{name} {shape}: rel err {err:.3e}"
+    strict = ctx.conv_layer(lid, x.cuda(), 0, relu=relu, pool=pool, cout=cout).cpu().numpy()
+    assert rel_err(strict, O.vgg_block(sd, name, x, k, relu, pool).numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("precision,tol", [("f16", FAST), ("bf16", 3e-2)])
+def test_forward_fast_vs_oracle(precision, tol):
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    sd = O.make_state_dict("superpoint", seed=21, logit_gain=6.0)
+    c = copy.deepcopy(SP_MODEL)
+    c["precision"] = precision
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    B, H, W = 2, 240, 320
+    x = torch.from_numpy(np.stack([smooth_image(H, W, 40 + i) for i in range(B)])[:, None])
+    want = O.model_forward(sd, x, SP_MODEL, dense_desc=False)
+    got = m(x.cuda())
+    e1 = rel_err(got["detector_output"]["logits"].cpu().numpy(), want["detector_output"]["logits"].numpy())
+    e2 = rel_err(got["detector_output"]["prob_heatmap"].cpu().numpy(), want["detector_output"]["prob_heatmap"].numpy())
+    e3 = rel_err(got["descriptor_output"]["desc_raw"].cpu().numpy(), want["descriptor_output"]["desc_raw"].numpy())
+    print(f"{precision}: logits {e1:.2e} prob {e2:.2e} desc_raw {e3:.2e}")
+    assert e1 < tol and e2 < tol and e3 < tol, (e1, e2, e3)
+
+
+def test_ha_fast_mode_keypoints_vs_golden(golden):
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import HomographyAdaptation
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    g = golden("ha_export.npz")
+    sd = O.make_state_dict("magicpoint", seed=int(g["seed"]), logit_gain=float(g["gain"]))
+    c = copy.deepcopy(MP_MODEL)
+    c["precision"] = "f16"
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    cfg = {"homography_adaptation": copy.deepcopy(HA_CFG), "model": c}
+    eng = HomographyAdaptation(cfg, m, "cuda")
+    heat, _ = eng.heatmaps(torch.from_numpy(g["image"]).cuda(), homographies=torch.from_numpy(g["H"]).view(1, 7, 3, 3))
+    err = rel_err(heat[0].cpu().numpy(), g["agg"])
+    a, b = keypoint_agreement(eng.keypoints(heat)[0], g["keypoints"])
+    print(f"fast-mode HA: heatmap rel err {err:.2e}, keypoints within 1px {a:.4f}/{b:.4f}")
+    assert err < 2e-2
+    assert a >= 0.97 and b >= 0.97
