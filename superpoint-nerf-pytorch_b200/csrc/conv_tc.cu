@@ -104,6 +104,31 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+// same instruction, descriptors given as (lo, hi) words so that only `lo` changes between the MMAs of a tile
+__device__ __forceinline__ void umma_f16_2w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // SWIZZLE_NONE K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -140,6 +165,7 @@ __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int is_bf16) {
 }
 
 // ------------------------------------------------------------------------------------------------ main kernel
+template <int TAPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -148,10 +174,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   __shared__ float bias_s[64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int halo = p.taps == 9 ? 1 : 0;
-  const int PW = kTW + 2 * halo, PH = kTH + 2 * halo;
-  const uint32_t ch_stride = (uint32_t)PH * PW * 16;     // bytes between 8-channel groups inside a slab
-  const int wbytes = p.cin_blocks * p.taps * kWBlockBytes;
+  constexpr int halo = TAPS == 9 ? 1 : 0;
+  constexpr int PW = kTW + 2 * halo, PH = kTH + 2 * halo;
+  constexpr uint32_t ch_stride = (uint32_t)PH * PW * 16;  // bytes between 8-channel groups inside a slab
+  const int wbytes = p.cin_blocks * TAPS * kWBlockBytes;
   uint8_t* wsm = smem;                                    // this CTA's weight slice, resident for the whole kernel
   uint8_t* slab0 = smem + ((wbytes + 1023) & ~1023);
 
@@ -177,64 +203,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_expect_tx(&bar_w, (uint32_t)wbytes);
       const uint8_t* wsrc = (const uint8_t*)p.wimg + (size_t)slice * wbytes;
       for (int o = 0; o < wbytes; o += kWBlockBytes) bulk_load(wsm + o, wsrc + o, kWBlockBytes, &bar_w);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = cta_in_slice; t < n_tiles; t += ctas_per_slice) {
-        const int n = t / tiles_per_img, r = t - n * tiles_per_img;
-        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        for (int cb = 0; cb < p.cin_blocks; ++cb) {
-          mbar_wait(&bar_empty[stage], phase ^ 1);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = cta_in_slice; t < n_tiles; t += ctas_per_slice) {
+      const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        mbar_wait(&bar_empty[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&bar_full[stage], (uint32_t)p.slab_bytes);
           tma_load_4d(slab0 + (size_t)stage * p.stage_bytes, &tmap, &bar_full[stage], (tx * kTW - halo) * 8,
                       ty * kTH - halo, cb * 8, n);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, N=64, M=128
-      const uint32_t fmt = p.is_bf16 ? 1u : 0u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_lbo = (p.dbg & 1) ? (uint32_t)PW * 16 : ch_stride, a_sbo = (p.dbg & 1) ? ch_stride : (uint32_t)PW * 16;
-      const uint32_t b_lbo = (p.dbg & 2) ? 128u : 1024u, b_sbo = (p.dbg & 2) ? 1024u : 128u;
-      mbar_wait(&bar_w, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const uint32_t w_addr = smem_u32(wsm);
-      for (int t = cta_in_slice; t < n_tiles; t += ctas_per_slice) {
-        mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (warp-uniform loop; descriptors differ only in their low word) =====================
+    // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, N=64, M=128
+    const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_lbo = (p.dbg & 1) ? (uint32_t)PW * 16 : ch_stride, a_sbo = (p.dbg & 1) ? ch_stride : (uint32_t)PW * 16;
+    const uint32_t b_lbo = (p.dbg & 2) ? 128u : 1024u, b_sbo = (p.dbg & 2) ? 1024u : 128u;
+    const uint32_t a_hi = (a_sbo >> 4) | (1u << 14), b_hi = (b_sbo >> 4) | (1u << 14);  // SBO | descriptor version 1
+    const uint32_t a_lo_c = (a_lbo >> 4) << 16, b_lo_c = (b_lbo >> 4) << 16;
+    mbar_wait(&bar_w, 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t w_addr = smem_u32(wsm), slab_addr = smem_u32(slab0);
+    for (int t = cta_in_slice; t < n_tiles; t += ctas_per_slice) {
+      mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 64;
+      for (int cb = 0; cb < p.cin_blocks; ++cb) {
+        mbar_wait(&bar_full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 64;
-        uint32_t accumulate = 0;
-        for (int cb = 0; cb < p.cin_blocks; ++cb) {
-          mbar_wait(&bar_full[stage], phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(slab0 + (size_t)stage * p.stage_bytes);
-          for (int tap = 0; tap < p.taps; ++tap) {
-            const int ky = p.taps == 9 ? tap / 3 : 0, kx = p.taps == 9 ? tap - ky * 3 : 0;
-            const uint32_t a_tap = a_base + (uint32_t)(ky * PW + kx) * 16;
-            const uint32_t b_tap = w_addr + (uint32_t)(cb * p.taps + tap) * kWBlockBytes;
+        const uint32_t a_lo = ((slab_addr + (uint32_t)stage * p.stage_bytes) >> 4) | a_lo_c;
+        const uint32_t b_lo = ((w_addr + (uint32_t)cb * (TAPS * kWBlockBytes)) >> 4) | b_lo_c;
+        if (elect_one()) {
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const int ky = TAPS == 9 ? tap / 3 : 0, kx = TAPS == 9 ? tap % 3 : 0;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t ad = smem_desc(a_tap + (uint32_t)kk * 2 * ch_stride, a_lbo, a_sbo);
-              const uint64_t bd = smem_desc(b_tap + (uint32_t)kk * 2048, b_lbo, b_sbo);
-              umma_f16(d_tmem, ad, bd, idesc, accumulate);
-              accumulate = 1;
+              const uint32_t aoff = ((uint32_t)(ky * PW + kx) * 16 + (uint32_t)kk * 2 * ch_stride) >> 4;
+              const uint32_t boff = ((uint32_t)tap * kWBlockBytes + (uint32_t)kk * 2048) >> 4;
+              umma_f16_2w(d_tmem, a_lo + aoff, a_hi, b_lo + boff, b_hi, idesc, (cb | tap | kk) ? 1u : 0u);
             }
           }
           umma_commit(&bar_empty[stage]);  // frees the slab once these MMAs have read it
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (cb == p.cin_blocks - 1) umma_commit(&bar_tfull[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&bar_tfull[acc]);      // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (4 warps; warp%4 selects the TMEM lane quarter) =====================
@@ -473,14 +503,15 @@ int launch_conv_tc(spn_ctx* ctx, int layer, int mode, const void* in, void* out,
     spn_set_error("cuTensorMapEncodeTiled failed (%d) for layer %d, %dx%dx%d", (int)cr, layer, L.cin, H, W);
     return SPN_E_CUDA;
   }
-  SPN_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  auto kern = L.ks == 3 ? conv_tc_kernel<9> : conv_tc_kernel<1>;
+  SPN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   const long long work = (long long)n_img * p.tiles_x * p.tiles_y * p.cout_slices;
   int grid = ctx->sm_count;
   if (work < grid) grid = (int)work;
   grid = grid / p.cout_slices * p.cout_slices;
   if (grid < p.cout_slices) grid = p.cout_slices;
   SpnProfScope prof(ctx, layer, s);
-  conv_tc_kernel<<<grid, kThreads, dyn, s>>>(tmap, p);
+  kern<<<grid, kThreads, dyn, s>>>(tmap, p);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }
