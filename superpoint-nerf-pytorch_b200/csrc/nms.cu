@@ -14,7 +14,11 @@
 // >= 148 images); status bytes live in a caller-invisible scratch buffer and stay L1/L2 resident.
 #include <math.h>
 
+#include <cooperative_groups.h>
+
 #include "spn_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -23,6 +27,7 @@ constexpr int kThreads = 1024;
 
 struct NmsFoot {
   int n;
+  int r;  // max |offset|
   int8_t dy[kMaxFoot];
   int8_t dx[kMaxFoot];
 };
@@ -63,46 +68,105 @@ __device__ __forceinline__ int block_excl_scan_flag(bool flag, int* s_warp, int*
   return base + within;
 }
 
+// Phase 1: greedy NMS as a parallel fixed point, all SMs cooperating on the whole batch.
+// Work unit = 32x32 pixel tile (one thread per pixel) with a halo of `foot.r` pixels staged in shared memory
+// (scores + status bytes, coalesced loads).  Inside a tile the rule is iterated to a local fixed point with the halo
+// frozen - every deduction made that way is valid for the global fixed point, pixels that depend on a still
+// undecided halo neighbour simply stay pending - then the tile's statuses are written back and the grid
+// synchronises; rounds repeat until no pixel of any image is pending.
 __global__ void __launch_bounds__(kThreads)
-box_nms_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ status_all, NmsFoot foot, int H, int W,
-               float min_prob, int top_k, float det_thresh, float* __restrict__ nms_all, int32_t* __restrict__ pred_all,
-               int32_t* __restrict__ kp_all, int32_t* __restrict__ kp_count, int max_kp) {
+nms_rounds_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ status_all, NmsFoot foot, int B, int H, int W,
+                  float min_prob, int tiles_x, int tiles_y, unsigned* __restrict__ pend) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) uint8_t nms_smem[];
+  const int r = foot.r, HT = 32 + 2 * r, HP = HT + 1;
+  float* sc = reinterpret_cast<float*>(nms_smem);            // [HT][HP]
+  uint8_t* st = nms_smem + (size_t)HT * HP * sizeof(float);  // [HT][HP]
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const size_t P = (size_t)H * W;
+  const int n_tiles = B * tiles_x * tiles_y;
+
+  for (size_t i = (size_t)blockIdx.x * kThreads + tid; i < (size_t)B * P; i += (size_t)gridDim.x * kThreads)
+    status_all[i] = (__ldg(&prob_all[i]) >= min_prob) ? 1 : 0;
+  if (blockIdx.x == 0 && tid < 3) pend[tid] = 0;
+  grid.sync();
+
+  for (int round = 0;; ++round) {
+    bool pending = false;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int b = tile / (tiles_x * tiles_y), rem = tile - b * (tiles_x * tiles_y);
+      const int y0 = (rem / tiles_x) * 32 - r, x0 = (rem % tiles_x) * 32 - r;
+      const float* prob = prob_all + (size_t)b * P;
+      uint8_t* status = status_all + (size_t)b * P;
+      bool any_undecided = false;
+      for (int i = tid; i < HT * HT; i += kThreads) {
+        const int hy = i / HT, hx = i - hy * HT;
+        const int y = y0 + hy, x = x0 + hx;
+        uint8_t v = 0;
+        float s = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+          v = __ldcg(&status[(size_t)y * W + x]);
+          if (v == 1) s = __ldg(&prob[(size_t)y * W + x]);
+          any_undecided |= (v == 1) && hy >= r && hy < HT - r && hx >= r && hx < HT - r;
+        }
+        st[hy * HP + hx] = v;
+        sc[hy * HP + hx] = s;
+      }
+      if (!__syncthreads_or(any_undecided)) continue;  // tile already decided (also orders the smem fill)
+      const int cy = ty + r, cx = tx + r;
+      const int gy = y0 + cy, gx = x0 + cx;
+      const int me = cy * HP + cx;
+      const float sp = sc[me];
+      for (int it = 0; it < 64; ++it) {
+        bool changed = false;
+        if (st[me] == 1) {
+          int res = 2;
+          for (int k = 0; k < foot.n; ++k) {
+            const int dy = foot.dy[k], dx = foot.dx[k];
+            const int q = me + dy * HP + dx;
+            const uint8_t v = st[q];
+            if (v == 2) { res = 0; break; }
+            if (v == 1) {
+              const float sq = sc[q];
+              if (sq > sp || (sq == sp && (dy < 0 || (dy == 0 && dx < 0)))) res = 1;
+            }
+          }
+          if (res != 1) { st[me] = (uint8_t)res; changed = true; }
+        }
+        if (!__syncthreads_or(changed)) break;
+      }
+      if (gy < H && gx < W) {
+        const uint8_t v = st[me];
+        status[(size_t)gy * W + gx] = v;
+        pending |= (v == 1);
+      }
+      __syncthreads();  // smem is reused by the next tile
+    }
+    const bool blk_pending = __syncthreads_or(pending);
+    if (tid == 0) {
+      if (blk_pending) atomicAdd(&pend[round % 3], 1u);
+      // slot (round+1)%3 was last read after the grid.sync of round-2; every CTA has since passed the sync of
+      // round-1, so it is safe to clear it here for its next use in round+1
+      if (blockIdx.x == 0) pend[(round + 1) % 3] = 0;
+    }
+    grid.sync();
+    if (__ldcg(&pend[round % 3]) == 0) break;
+  }
+}
+
+// Phase 2 (one CTA per image): optional top-k, scattered / thresholded maps, row-major keypoint list.
+__global__ void __launch_bounds__(kThreads)
+nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ status_all, int H, int W, int top_k,
+                    float det_thresh, float* __restrict__ nms_all, int32_t* __restrict__ pred_all,
+                    int32_t* __restrict__ kp_all, int32_t* __restrict__ kp_count, int max_kp) {
   __shared__ int s_warp[kThreads / 32];
   __shared__ unsigned s_hist[256];
   __shared__ unsigned s_sel[2];
   const int b = blockIdx.x;
   const int P = H * W;
   const float* prob = prob_all + (size_t)b * P;
-  volatile uint8_t* status = status_all + (size_t)b * P;
+  uint8_t* status = status_all + (size_t)b * P;
   const int tid = threadIdx.x;
-
-  for (int p = tid; p < P; p += kThreads) status[p] = (__ldg(&prob[p]) >= min_prob) ? 1 : 0;
-  __syncthreads();
-
-  // ---- greedy NMS as a parallel fixed point ----
-  while (true) {
-    bool pending = false;
-    for (int p = tid; p < P; p += kThreads) {
-      if (status[p] != 1) continue;
-      const int y = p / W, x = p - y * W;
-      const float sp = __ldg(&prob[p]);
-      int res = 2;
-      for (int k = 0; k < foot.n; ++k) {
-        const int yy = y + foot.dy[k], xx = x + foot.dx[k];
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const int q = yy * W + xx;
-        const uint8_t st = status[q];
-        if (st == 2) { res = 0; break; }
-        if (st == 1) {
-          const float sq = __ldg(&prob[q]);
-          if (sq > sp || (sq == sp && q < p)) res = 1;
-        }
-      }
-      if (res == 1) pending = true;
-      else status[p] = (uint8_t)res;
-    }
-    if (!__syncthreads_or(pending)) break;
-  }
 
   // ---- optional top-k over the survivors: (score desc, index asc) ----
   if (top_k > 0) {
@@ -211,12 +275,30 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
         foot.dx[foot.n] = (int8_t)dx;
         foot.n++;
       }
+  foot.r = 0;
+  for (int k = 0; k < foot.n; ++k) foot.r = max(foot.r, max(abs((int)foot.dy[k]), abs((int)foot.dx[k])));
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = spn_ensure_aux(ctx, (size_t)B * H * W, s);
+  SPN_CUDA(cudaSetDevice(ctx->device));
+  const size_t status_bytes = ((size_t)B * H * W + 255) & ~(size_t)255;
+  int rc = spn_ensure_aux(ctx, status_bytes + 256, s);
   if (rc) return rc;
+  uint8_t* status = (uint8_t*)ctx->aux;
+  unsigned* pend = (unsigned*)(ctx->aux + status_bytes);
+  const int HT = 32 + 2 * foot.r;
+  const size_t smem = (size_t)HT * (HT + 1) * 5 + 16;
+  int per_sm = 0;
+  SPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_rounds_kernel, kThreads, smem));
+  SPN_REQUIRE(per_sm >= 1, "spn_box_nms_topk: cooperative kernel does not fit on an SM");
+  int tiles_x = spn_cdiv(W, 32), tiles_y = spn_cdiv(H, 32);
+  const long long n_tiles = (long long)B * tiles_x * tiles_y;
+  int grid = per_sm * ctx->sm_count;
+  if (n_tiles < grid) grid = (int)n_tiles;
   SpnProfScope prof(ctx, SPN_PROF_NMS, s);
-  box_nms_kernel<<<B, kThreads, 0, s>>>(d_prob, (uint8_t*)ctx->aux, foot, H, W, min_prob, top_k, det_thresh, d_nms,
-                                        d_pred, d_kp, d_kp_count, max_kp);
+  void* args[] = {(void*)&d_prob, (void*)&status, (void*)&foot, (void*)&B, (void*)&H, (void*)&W, (void*)&min_prob,
+                  (void*)&tiles_x, (void*)&tiles_y, (void*)&pend};
+  SPN_CUDA(cudaLaunchCooperativeKernel((void*)nms_rounds_kernel, dim3(grid), dim3(kThreads), args, smem, s));
+  ctx->launches++;
+  nms_finalize_kernel<<<B, kThreads, 0, s>>>(d_prob, status, H, W, top_k, det_thresh, d_nms, d_pred, d_kp, d_kp_count, max_kp);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }
