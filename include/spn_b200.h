@@ -106,6 +106,10 @@ SPN_API int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H, in
                      int top_k, float det_thresh, float* d_nms, int32_t* d_pred, int32_t* d_kp, int32_t* d_kp_count,
                      int max_kp, spn_stream stream);
 
+/* Statistics of the last spn_box_nms_topk call with the same (B,H,W): h_out[0] = global rounds (grid-wide
+ * synchronisations), h_out[1] = tile-local iterations, h_out[2] = tile visits.  Synchronises the device. */
+SPN_API int spn_nms_stats(spn_ctx* ctx, int B, int H, int W, int64_t* h_out);
+
 /* ExportDetections.step warp part (export.py:51-66): for every image i < n_images and homography j < n_h
  *   slot = i*(n_h+1) + 1 + j : d_warped[slot] = warp_perspective(image_i, H_ij, bilinear, align_corners=True)
  *                              d_mask[slot]   = erosion(warp_perspective(ones, H_ij, nearest), ellipse(2*margin))

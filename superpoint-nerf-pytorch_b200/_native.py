@@ -48,6 +48,7 @@ PROTOTYPES = {
     "spn_dense_descriptors": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "spn_sample_descriptors": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "spn_box_nms_topk": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    "spn_nms_stats": (_i, [_vp, _i, _i, _i, _vp]),
     "spn_warp_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "spn_ha_aggregate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "spn_sample_homographies": (_i, [_vp, C.POINTER(HomographyParams), C.c_uint64, C.c_uint64, _i, _i, _i, _vp, _vp, _vp]),
@@ -236,6 +237,11 @@ class Context:
                    int(top_k), C.c_float(det), _ptr(out["nms"]), _ptr(out["pred"]), _ptr(out["kp"]), _ptr(out["kp_count"]),
                    int(max_kp), _stream())
         return out
+
+    def nms_stats(self, B, H, W):
+        out = (C.c_int64 * 4)()
+        self._call("spn_nms_stats", self.handle, B, H, W, C.cast(out, C.c_void_p))
+        return {"global_rounds": int(out[0]), "local_iterations": int(out[1]), "tile_visits": int(out[2])}
 
     # ---- homography adaptation -------------------------------------------------------------------
     def warp_batch(self, images, hinv, margin):

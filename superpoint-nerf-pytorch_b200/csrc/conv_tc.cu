@@ -342,39 +342,60 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ CUDA-core helpers
-// block_1 (Cin = 1): fp32 image -> C8 16-bit activations, 64 channels.  K = 9 is too small for a tensor-core tile.
+// block_1 (Cin = 1): fp32 image -> C8 16-bit activations, 64 channels.  K = 9 is too small for a tensor-core tile;
+// the kernel is bound by the 128 B/pixel it writes.  One warp = one 8-channel group (its 72 folded weights live in
+// registers), lane = pixel, kPx pixels per thread at stride 32 so that every store instruction writes 512 contiguous
+// bytes; the 3x3 input window comes from a shared-memory row tile.
+constexpr int kC1Px = 5;  // 160 pixels per block row: 320 = 2 blocks, 160 = 1 block
 __global__ void __launch_bounds__(256)
 conv1_c8_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9][64]*/, const float* __restrict__ bias,
                 void* __restrict__ out, int B, int H, int W, int is_bf16) {
-  __shared__ float ws[9 * 64 + 64];
-  for (int i = threadIdx.x; i < 9 * 64 + 64; i += blockDim.x) ws[i] = i < 576 ? w[i] : bias[i - 576];
-  __syncthreads();
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int cg = threadIdx.x >> 5;  // channel group 0..7
-  const int y = blockIdx.y, n = blockIdx.z;
-  if (x >= W) return;
+  constexpr int TWp = 32 * kC1Px;
+  __shared__ float rows[3][TWp + 2];
+  __shared__ __align__(16) float ws[9 * 64 + 64];
+  const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;  // channel group 0..7
+  const int x0 = blockIdx.x * TWp, y = blockIdx.y, n = blockIdx.z;
   const float* im = img + (size_t)n * H * W;
-  float in[9];
+  for (int i = threadIdx.x; i < 9 * 64 + 64; i += 256) ws[i] = i < 576 ? __ldg(&w[i]) : __ldg(&bias[i - 576]);
+  for (int i = threadIdx.x; i < 3 * (TWp + 2); i += 256) {
+    const int r = i / (TWp + 2), c = i - r * (TWp + 2);
+    const int yy = y + r - 1, xx = x0 + c - 1;
+    rows[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(&im[(size_t)yy * W + xx]) : 0.f;
+  }
+  __syncthreads();
+  float wr[9][8], bb[8];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+  for (int t = 0; t < 9; ++t) {
+    const float4 a = *reinterpret_cast<const float4*>(&ws[t * 64 + cg * 8]);
+    const float4 b = *reinterpret_cast<const float4*>(&ws[t * 64 + cg * 8 + 4]);
+    wr[t][0] = a.x; wr[t][1] = a.y; wr[t][2] = a.z; wr[t][3] = a.w;
+    wr[t][4] = b.x; wr[t][5] = b.y; wr[t][6] = b.z; wr[t][7] = b.w;
+  }
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int yy = y + ky - 1, xx = x + kx - 1;
-      in[ky * 3 + kx] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(&im[(size_t)yy * W + xx]) : 0.f;
-    }
-  float acc[8];
+  for (int c = 0; c < 8; ++c) bb[c] = ws[576 + cg * 8 + c];
+  uint4* o = reinterpret_cast<uint4*>(out) + (((size_t)n * 8 + cg) * H + y) * W;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = ws[576 + cg * 8 + c];
+  for (int k = 0; k < kC1Px; ++k) {
+    const int xl = lane + 32 * k, x = x0 + xl;
+    if (x >= W) break;
+    float acc[8];
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+    for (int c = 0; c < 8; ++c) acc[c] = bb[c];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = fmaf(in[t], ws[t * 64 + cg * 8 + c], acc[c]);
-  uint4 o;
-  o.x = pack2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), is_bf16);
-  o.y = pack2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), is_bf16);
-  o.z = pack2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), is_bf16);
-  o.w = pack2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), is_bf16);
-  reinterpret_cast<uint4*>(out)[(((size_t)n * 8 + cg) * H + y) * W + x] = o;
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float v = rows[ky][xl + kx];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, wr[ky * 3 + kx][c], acc[c]);
+      }
+    uint4 q;
+    q.x = pack2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), is_bf16);
+    q.y = pack2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), is_bf16);
+    q.z = pack2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), is_bf16);
+    q.w = pack2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), is_bf16);
+    o[x] = q;
+  }
 }
 
 // layout conversions for the single-layer entry point (spn_conv_layer): NCHW fp32 <-> C8 16-bit
@@ -588,7 +609,7 @@ int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int
   const int bf = mode == SPN_MODE_BF16 ? 1 : 0;
   {
     SpnProfScope prof(ctx, SPN_L_BLOCK1, s);
-    dim3 g(spn_cdiv(W, 32), H, B);
+    dim3 g(spn_cdiv(W, 32 * kC1Px), H, B);
     conv1_c8_kernel<<<g, 256, 0, s>>>(d_images, st->w1, ctx->layers[0].bias, A, B, H, W, bf);
     SPN_CHECK_LAUNCH(ctx);
   }

@@ -80,37 +80,85 @@ __device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, fl
   return v;
 }
 
-// Raw (un-eroded) validity of the tile + halo for matrix m; pixels outside the image count as valid (geodesic).
-__device__ __forceinline__ void fill_raw(uint8_t (*raw)[kRawW], const float* m, const ErodeK& ek, int tx0, int ty0,
-                                         int H, int W) {
+// ---- tile classification -----------------------------------------------------------------------------------
+// The set of pixels p whose source coordinate M p satisfies a bound (sx >= a, sx <= b, ...) is a half-plane in p as
+// long as the homogeneous z stays positive, so for a rectangle of pixels it suffices to test its four corners:
+//   all four corners inside the source image (with a safety margin)  -> every pixel of the rectangle is valid,
+//   all four corners beyond the same source edge (with a margin)     -> every pixel is invalid and samples to zero.
+// Only tiles cut by the border of the warped quad need the per-pixel validity bits and the erosion.
+enum { kTileMixed = 0, kTileInside = 1, kTileOutside = 2 };
+
+__device__ __forceinline__ int classify_tile(const float* m, const ErodeK& ek, int tx0, int ty0, int H, int W) {
+  const int lane = threadIdx.x & 31;
+  // halo rectangle clipped to the image (out-of-image neighbours never erode: geodesic border)
+  const int xa = max(tx0 - ek.org, 0), xb = min(tx0 + kTileW - 1 + (ek.ks - ek.org - 1), W - 1);
+  const int ya = max(ty0 - ek.org, 0), yb = min(ty0 + kTileH - 1 + (ek.ks - ek.org - 1), H - 1);
+  const float x = (lane & 1) ? (float)xb : (float)xa, y = (lane & 2) ? (float)yb : (float)ya;
+  const float nx = fmaf(m[0], x, fmaf(m[1], y, m[2]));
+  const float ny = fmaf(m[3], x, fmaf(m[4], y, m[5]));
+  const float z = fmaf(m[6], x, fmaf(m[7], y, m[8]));
+  const float sc = 1.0f / (z + 1e-8f);
+  const float sx = nx * sc, sy = ny * sc;
+  const float mg = 1e-2f;
+  const bool zok = z > 1e-3f;
+  const bool in = zok && sx >= -0.5f + mg && sx <= (float)W - 0.5f - mg && sy >= -0.5f + mg && sy <= (float)H - 0.5f - mg;
+  const unsigned c4 = 0xFu;
+  const unsigned b_z = __ballot_sync(0xffffffffu, zok) & c4;
+  const unsigned b_in = __ballot_sync(0xffffffffu, in) & c4;
+  const unsigned b_l = __ballot_sync(0xffffffffu, sx < -1.0f - mg) & c4;
+  const unsigned b_r = __ballot_sync(0xffffffffu, sx > (float)W + mg) & c4;
+  const unsigned b_t = __ballot_sync(0xffffffffu, sy < -1.0f - mg) & c4;
+  const unsigned b_b = __ballot_sync(0xffffffffu, sy > (float)H + mg) & c4;
+  if (b_z != c4) return kTileMixed;
+  if (b_in == c4) return kTileInside;
+  if (b_l == c4 || b_r == c4 || b_t == c4 || b_b == c4) return kTileOutside;
+  return kTileMixed;
+}
+
+// Raw (un-eroded) validity bits of the tile + halo, linearised row-major (rw = kTileW + ks - 1 columns), one ballot
+// per 32 positions; positions outside the image count as valid (geodesic border).
+constexpr int kRawWords = (kRawH * kRawW + 31) / 32 + 1;
+
+__device__ __forceinline__ void fill_raw_bits(uint32_t* bits, const float* m, const ErodeK& ek, int tx0, int ty0, int H,
+                                              int W) {
   const int rh = kTileH + ek.ks - 1, rw = kTileW + ek.ks - 1;
-  for (int i = threadIdx.x; i < rh * rw; i += blockDim.x) {
-    const int ry = i / rw, rx = i - ry * rw;
-    const int y = ty0 + ry - ek.org, x = tx0 + rx - ek.org;
-    int v = 1;
-    if (x >= 0 && x < W && y >= 0 && y < H) {
-      float sx, sy;
-      apply_h(m, (float)x, (float)y, sx, sy);
-      v = inside_nearest(sx, sy, H, W);
+  const int n = rh * rw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int base = warp * 32; base < n + 32; base += nwarps * 32) {  // + 32: one zero-padded word past the end
+    const int i = base + lane;
+    int v = 0;
+    if (i < n) {
+      const int ry = i / rw, rx = i - ry * rw;
+      const int y = ty0 + ry - ek.org, x = tx0 + rx - ek.org;
+      v = 1;
+      if (x >= 0 && x < W && y >= 0 && y < H) {
+        float sx, sy;
+        apply_h(m, (float)x, (float)y, sx, sy);
+        v = inside_nearest(sx, sy, H, W);
+      }
     }
-    raw[ry][rx] = (uint8_t)v;
+    const unsigned b = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) bits[base >> 5] = b;
   }
 }
 
-__device__ __forceinline__ int eroded_at(const uint8_t (*raw)[kRawW], const ErodeK& ek, int tx, int ty) {
-  int m = 1;
+__device__ __forceinline__ int eroded_bits(const uint32_t* bits, const ErodeK& ek, int tx, int ty) {
+  const int rw = kTileW + ek.ks - 1;
+  int ok = 1;
   for (int i = 0; i < ek.ks; ++i) {
-    const uint32_t bits = ek.rows[i];
-    for (int j = 0; j < ek.ks; ++j)
-      if ((bits >> j) & 1u) m &= raw[ty + i][tx + j];
+    const int o = (ty + i) * rw + tx;
+    const uint32_t lo = bits[o >> 5], hi = bits[(o >> 5) + 1];
+    const uint32_t w = __funnelshift_r(lo, hi, o & 31);
+    const uint32_t rm = ek.rows[i];
+    ok &= ((w & rm) == rm);
   }
-  return m;
+  return ok;
 }
 
 __global__ void __launch_bounds__(256)
 warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hinv, int n_h, int H, int W,
                   int tiles_x, ErodeK ek, float* __restrict__ warped, uint8_t* __restrict__ mask) {
-  __shared__ uint8_t raw[kRawH][kRawW];
+  __shared__ uint32_t bits[kRawWords];
   __shared__ float m[9];
   const int slot = blockIdx.y;
   const int img = slot / (n_h + 1), j = slot - img * (n_h + 1);
@@ -119,8 +167,9 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hi
   const int x = tx0 + tx, y = ty0 + ty;
   const float* src = images + (size_t)img * H * W;
   const size_t o = ((size_t)slot * H + y) * W + x;
+  const bool in_img = x < W && y < H;
   if (j == 0) {  // identity forward (export.py:93): the image itself, no mask
-    if (x < W && y < H) {
+    if (in_img) {
       warped[o] = __ldg(&src[(size_t)y * W + x]);
       mask[o] = 1;
     }
@@ -128,13 +177,22 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hi
   }
   if (threadIdx.x < 9) m[threadIdx.x] = __ldg(&hinv[((size_t)img * n_h + (j - 1)) * 9 + threadIdx.x]);
   __syncthreads();
-  fill_raw(raw, m, ek, tx0, ty0, H, W);
-  __syncthreads();
-  if (x < W && y < H) {
+  const int cls = classify_tile(m, ek, tx0, ty0, H, W);  // identical in every warp of the block
+  if (cls == kTileOutside) {
+    if (in_img) { warped[o] = 0.f; mask[o] = 0; }
+    return;
+  }
+  int mk = 1;
+  if (cls == kTileMixed) {
+    fill_raw_bits(bits, m, ek, tx0, ty0, H, W);
+    __syncthreads();
+    mk = eroded_bits(bits, ek, tx, ty);
+  }
+  if (in_img) {
     float sx, sy;
     apply_h(m, (float)x, (float)y, sx, sy);
     warped[o] = bilinear_zero(src, sx, sy, H, W);
-    mask[o] = (uint8_t)eroded_at(raw, ek, tx, ty);
+    mask[o] = (uint8_t)mk;
   }
 }
 
@@ -142,7 +200,7 @@ __global__ void __launch_bounds__(256)
 ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ hmat, int n_h, int H, int W,
                     int tiles_x, ErodeK ek, int agg_max, float* __restrict__ out) {
   extern __shared__ float hs[];  // n_h * 9
-  __shared__ uint8_t raw[2][kRawH][kRawW];
+  __shared__ uint32_t bits[2][kRawWords];
   const int img = blockIdx.y;
   const int tx0 = (blockIdx.x % tiles_x) * kTileW, ty0 = (blockIdx.x / tiles_x) * kTileH;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -156,20 +214,25 @@ ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ h
     mx = acc;
   }
   __syncthreads();
+  int nmixed = 0;
   for (int j = 0; j < n_h; ++j) {
     const float* m = hs + j * 9;
-    uint8_t (*rb)[kRawW] = raw[j & 1];
-    fill_raw(rb, m, ek, tx0, ty0, H, W);
-    __syncthreads();
-    if (in_img) {
-      float v = 0.f;
-      if (eroded_at(rb, ek, tx, ty)) {
-        float sx, sy;
-        apply_h(m, (float)x, (float)y, sx, sy);
-        v = bilinear_zero(pimg + (size_t)(j + 1) * H * W, sx, sy, H, W);
-        acc += v;
-        cnt += 1.f;
-      }
+    const int cls = classify_tile(m, ek, tx0, ty0, H, W);  // block-uniform
+    if (cls == kTileOutside) continue;                      // count == 0 on the whole tile: contributes nothing
+    int c = 1;
+    if (cls == kTileMixed) {
+      uint32_t* bb = bits[nmixed & 1];  // double buffered: one barrier per mixed homography
+      ++nmixed;
+      fill_raw_bits(bb, m, ek, tx0, ty0, H, W);
+      __syncthreads();
+      c = eroded_bits(bb, ek, tx, ty);
+    }
+    if (in_img && c) {
+      float sx, sy;
+      apply_h(m, (float)x, (float)y, sx, sy);
+      const float v = bilinear_zero(pimg + (size_t)(j + 1) * H * W, sx, sy, H, W);
+      acc += v;
+      cnt += 1.f;
       mx = fmaxf(mx, v);
     }
   }

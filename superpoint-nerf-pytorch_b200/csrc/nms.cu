@@ -88,7 +88,7 @@ nms_rounds_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ stat
 
   for (size_t i = (size_t)blockIdx.x * kThreads + tid; i < (size_t)B * P; i += (size_t)gridDim.x * kThreads)
     status_all[i] = (__ldg(&prob_all[i]) >= min_prob) ? 1 : 0;
-  if (blockIdx.x == 0 && tid < 3) pend[tid] = 0;
+  if (blockIdx.x == 0 && tid < 8) pend[tid] = 0;
   grid.sync();
 
   for (int round = 0;; ++round) {
@@ -116,25 +116,62 @@ nms_rounds_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ stat
       const int cy = ty + r, cx = tx + r;
       const int gy = y0 + cy, gx = x0 + cx;
       const int me = cy * HP + cx;
-      const float sp = sc[me];
-      for (int it = 0; it < 64; ++it) {
-        bool changed = false;
-        if (st[me] == 1) {
-          int res = 2;
+      // Only higher-ranked candidate neighbours ("blockers") can decide this pixel: it is suppressed iff one of
+      // them is kept and kept iff all of them are suppressed.  Collect them once per visit as a bit mask.
+      uint64_t blockers = 0;
+      bool mine = st[me] == 1;
+      if (mine) {
+        const float sp = sc[me];
+        if (foot.n <= 64) {
           for (int k = 0; k < foot.n; ++k) {
             const int dy = foot.dy[k], dx = foot.dx[k];
             const int q = me + dy * HP + dx;
             const uint8_t v = st[q];
-            if (v == 2) { res = 0; break; }
+            if (v == 2) { blockers = 0; st[me] = 0; mine = false; break; }
             if (v == 1) {
               const float sq = sc[q];
-              if (sq > sp || (sq == sp && (dy < 0 || (dy == 0 && dx < 0)))) res = 1;
+              if (sq > sp || (sq == sp && (dy < 0 || (dy == 0 && dx < 0)))) blockers |= 1ull << k;
             }
           }
-          if (res != 1) { st[me] = (uint8_t)res; changed = true; }
+          if (mine && blockers == 0) { st[me] = 2; mine = false; }
+        }
+      }
+      __syncthreads();
+      for (int it = 0; it < 256; ++it) {
+        bool changed = false;
+        if (mine) {
+          if (foot.n <= 64) {
+            uint64_t rem = blockers;
+            int res = 1;
+            while (rem) {
+              const int k = __ffsll((long long)rem) - 1;
+              rem &= rem - 1;
+              const uint8_t v = st[me + foot.dy[k] * HP + foot.dx[k]];
+              if (v == 2) { res = 0; break; }
+              if (v == 0) blockers &= ~(1ull << k);
+            }
+            if (res == 1 && blockers == 0) res = 2;
+            if (res != 1) { st[me] = (uint8_t)res; mine = false; changed = true; }
+          } else {  // large footprints (box size > 4): full scan every iteration
+            const float sp = sc[me];
+            int res = 2;
+            for (int k = 0; k < foot.n; ++k) {
+              const int dy = foot.dy[k], dx = foot.dx[k];
+              const int q = me + dy * HP + dx;
+              const uint8_t v = st[q];
+              if (v == 2) { res = 0; break; }
+              if (v == 1) {
+                const float sq = sc[q];
+                if (sq > sp || (sq == sp && (dy < 0 || (dy == 0 && dx < 0)))) res = 1;
+              }
+            }
+            if (res != 1) { st[me] = (uint8_t)res; mine = false; changed = true; }
+          }
         }
         if (!__syncthreads_or(changed)) break;
+        if (tid == 0) atomicAdd(&pend[4], 1u);  // statistics: local iterations
       }
+      if (tid == 0) atomicAdd(&pend[5], 1u);    // statistics: tile visits with undecided pixels
       if (gy < H && gx < W) {
         const uint8_t v = st[me];
         status[(size_t)gy * W + gx] = v;
@@ -150,6 +187,7 @@ nms_rounds_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ stat
       if (blockIdx.x == 0) pend[(round + 1) % 3] = 0;
     }
     grid.sync();
+    if (blockIdx.x == 0 && tid == 0) pend[3] = (unsigned)round + 1;  // statistics: global rounds
     if (__ldcg(&pend[round % 3]) == 0) break;
   }
 }
@@ -228,34 +266,61 @@ nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ st
   }
 
   // ---- outputs: scattered map, thresholded map, row-major keypoint list ----
+  // Warp w owns the contiguous pixel range [w*seg, (w+1)*seg): pass 1 counts its keypoints (no barriers, loads in
+  // flight back to back), one block scan orders the 32 warps, pass 2 writes maps and keypoints in row-major order.
   float* nms = nms_all ? nms_all + (size_t)b * P : nullptr;
   int32_t* pred = pred_all ? pred_all + (size_t)b * P : nullptr;
   int32_t* kp = kp_all ? kp_all + (size_t)b * max_kp * 2 : nullptr;
-  int kp_base = 0;
-  for (int base = 0; base < P; base += kThreads) {
-    const int p = base + tid;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int seg = ((P + kThreads - 1) / kThreads) * 32;  // multiple of 32
+  const int p_begin = warp * seg, p_end = min(P, p_begin + seg);
+  int cnt = 0;
+  for (int p = p_begin + lane; p < p_end; p += 32) {
+    const float v = (status[p] == 2) ? __ldg(&prob[p]) : 0.0f;
+    cnt += (v >= det_thresh);
+  }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  __syncthreads();
+  if (lane == 0) s_warp[warp] = cnt;
+  __syncthreads();
+  int base = 0, total = 0;
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int c = s_warp[w];
+    if (w < warp) base += c;
+    total += c;
+  }
+  for (int p0 = p_begin; p0 < p_end; p0 += 32) {
+    const int p = p0 + lane;
     bool is_kp = false;
-    if (p < P) {
+    if (p < p_end) {
       const float v = (status[p] == 2) ? __ldg(&prob[p]) : 0.0f;
       is_kp = v >= det_thresh;
       if (nms) nms[p] = v;
       if (pred) pred[p] = is_kp ? 1 : 0;
     }
-    if (kp || kp_count) {
-      int tot;
-      const int rank = block_excl_scan_flag(is_kp, s_warp, &tot);
-      if (is_kp && kp && kp_base + rank < max_kp) {
-        const int y = p / W;
-        kp[2 * (kp_base + rank)] = y;
-        kp[2 * (kp_base + rank) + 1] = p - y * W;
-      }
-      kp_base += tot;
+    const unsigned bal = __ballot_sync(0xffffffffu, is_kp);
+    const int rank = base + __popc(bal & ((1u << lane) - 1u));
+    if (is_kp && kp && rank < max_kp) {
+      const int y = p / W;
+      kp[2 * rank] = y;
+      kp[2 * rank + 1] = p - y * W;
     }
+    base += __popc(bal);
   }
-  if (kp_count && tid == 0) kp_count[b] = kp_base;
+  if (kp_count && tid == 0) kp_count[b] = total;
 }
 
 }  // namespace
+
+extern "C" int spn_nms_stats(spn_ctx* ctx, int B, int H, int W, int64_t* h_out) {
+  SPN_REQUIRE(ctx && h_out && ctx->aux, "spn_nms_stats: nothing to read");
+  const size_t status_bytes = ((size_t)B * H * W + 255) & ~(size_t)255;
+  unsigned v[8];
+  SPN_CUDA(cudaDeviceSynchronize());
+  SPN_CUDA(cudaMemcpy(v, ctx->aux + status_bytes, sizeof(v), cudaMemcpyDeviceToHost));
+  h_out[0] = v[3]; h_out[1] = v[4]; h_out[2] = v[5];
+  return SPN_OK;
+}
 
 extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H, int W, float size, float iou,
                                 float min_prob, int top_k, float det_thresh, float* d_nms, int32_t* d_pred,
