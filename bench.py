@@ -172,7 +172,7 @@ def run_native(args):
     mcfg = dict(copy.deepcopy(MODEL_CFG), precision=args.precision)
     model = get_model(mcfg, dev).eval()
     model.load_state_dict(random_init_state_dict())  # random-init weights (no checkpoints ship with the reference)
-    ha = dict(copy.deepcopy(HA_CFG), sampler="device", seed=1234, max_forwards=args.max_forwards)
+    ha = dict(copy.deepcopy(HA_CFG), sampler="device", seed=1234, max_forwards=args.max_forwards, streams=args.streams)
     cfg = {"homography_adaptation": ha, "model": mcfg}
     eng = HomographyAdaptation(cfg, model, dev)
     ctx = model.native()
@@ -212,9 +212,20 @@ def run_native(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ctx.profile_enable(True)
-    ctx.profile_read()
-    l0 = ctx.launches
+    ctxs = list(model._ctxs.values())     # one context per concurrent stream
+
+    def prof_read_all():
+        tot = {}
+        for c in ctxs:
+            for k, (t, n) in c.profile_read().items():
+                a = tot.get(k, (0.0, 0))
+                tot[k] = (a[0] + t, a[1] + n)
+        return tot
+
+    for c in ctxs:
+        c.profile_enable(True)
+    prof_read_all()
+    l0 = sum(c.launches for c in ctxs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     kept = 0
@@ -223,9 +234,10 @@ def run_native(args):
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = ctx.launches - l0
-    prof = ctx.profile_read()
-    ctx.profile_enable(False)
+    launches = sum(c.launches for c in ctxs) - l0
+    prof = prof_read_all()
+    for c in ctxs:
+        c.profile_enable(False)
     clocks = sampler.stop() if sampler else None
     kept = int(r["kp_count"].sum().item())
     value = world * ips * args.steps / (ms / 1e3)
@@ -294,7 +306,7 @@ def run_native(args):
             "dtype": {"fp32": "f32", "f16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": "MagicPoint HA pseudo-label export, 240x320, 100 homographies (configs[1])",
                        "images_per_step_per_gpu": ips, "forwards_per_step_per_gpu": ips * NUM_H, "precision": args.precision,
-                       "weights": "random-init", "sampler": "device", "parallelism": f"image-sharded x{world}",
+                       "weights": "random-init", "sampler": "device", "streams": args.streams, "parallelism": f"image-sharded x{world}",
                        "l2_policy": "no explicit flush: each step streams > 1 GB of fresh activations per GPU (>> 126 MB L2) "
                                     "and uses images not seen before"},
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": ips * H * W * 4,
@@ -319,6 +331,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SPN_B200_PRECISION", "fp32"), choices=["fp32", "f16", "bf16"])
     ap.add_argument("--images-per-step", type=int, default=4)
     ap.add_argument("--max-forwards", type=int, default=100)
+    ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--ref-homographies", type=int, default=6, help="homographies in the bounded CPU sample")
     ap.add_argument("--steps-ref", type=int, default=1)
     ap.add_argument("--warmup-ref", type=int, default=0)

@@ -346,20 +346,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
 // the kernel is bound by the 128 B/pixel it writes.  One warp = one 8-channel group (its 72 folded weights live in
 // registers), lane = pixel, kPx pixels per thread at stride 32 so that every store instruction writes 512 contiguous
 // bytes; the 3x3 input window comes from a shared-memory row tile.
-constexpr int kC1Px = 5;  // 160 pixels per block row: 320 = 2 blocks, 160 = 1 block
+constexpr int kC1Px = 5;   // 160 pixels per block row: 320 = 2 blocks, 160 = 1 block
+constexpr int kC1Rows = 8; // image rows per block (amortises the weight fetch)
 __global__ void __launch_bounds__(256)
 conv1_c8_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9][64]*/, const float* __restrict__ bias,
                 void* __restrict__ out, int B, int H, int W, int is_bf16) {
   constexpr int TWp = 32 * kC1Px;
-  __shared__ float rows[3][TWp + 2];
+  __shared__ float rows[kC1Rows + 2][TWp + 2];
   __shared__ __align__(16) float ws[9 * 64 + 64];
   const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;  // channel group 0..7
-  const int x0 = blockIdx.x * TWp, y = blockIdx.y, n = blockIdx.z;
+  const int x0 = blockIdx.x * TWp, y0 = blockIdx.y * kC1Rows, n = blockIdx.z;
   const float* im = img + (size_t)n * H * W;
   for (int i = threadIdx.x; i < 9 * 64 + 64; i += 256) ws[i] = i < 576 ? __ldg(&w[i]) : __ldg(&bias[i - 576]);
-  for (int i = threadIdx.x; i < 3 * (TWp + 2); i += 256) {
+  for (int i = threadIdx.x; i < (kC1Rows + 2) * (TWp + 2); i += 256) {
     const int r = i / (TWp + 2), c = i - r * (TWp + 2);
-    const int yy = y + r - 1, xx = x0 + c - 1;
+    const int yy = y0 + r - 1, xx = x0 + c - 1;
     rows[r][c] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(&im[(size_t)yy * W + xx]) : 0.f;
   }
   __syncthreads();
@@ -373,28 +374,32 @@ conv1_c8_kernel(const float* __restrict__ img, const float* __restrict__ w /*[9]
   }
 #pragma unroll
   for (int c = 0; c < 8; ++c) bb[c] = ws[576 + cg * 8 + c];
-  uint4* o = reinterpret_cast<uint4*>(out) + (((size_t)n * 8 + cg) * H + y) * W;
+  for (int ry = 0; ry < kC1Rows; ++ry) {
+    const int y = y0 + ry;
+    if (y >= H) break;
+    uint4* o = reinterpret_cast<uint4*>(out) + (((size_t)n * 8 + cg) * H + y) * W;
 #pragma unroll
-  for (int k = 0; k < kC1Px; ++k) {
-    const int xl = lane + 32 * k, x = x0 + xl;
-    if (x >= W) break;
-    float acc[8];
+    for (int k = 0; k < kC1Px; ++k) {
+      const int xl = lane + 32 * k, x = x0 + xl;
+      if (x >= W) break;
+      float acc[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = bb[c];
+      for (int c = 0; c < 8; ++c) acc[c] = bb[c];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float v = rows[ky][xl + kx];
+        for (int kx = 0; kx < 3; ++kx) {
+          const float v = rows[ry + ky][xl + kx];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, wr[ky * 3 + kx][c], acc[c]);
-      }
-    uint4 q;
-    q.x = pack2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), is_bf16);
-    q.y = pack2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), is_bf16);
-    q.z = pack2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), is_bf16);
-    q.w = pack2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), is_bf16);
-    o[x] = q;
+          for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, wr[ky * 3 + kx][c], acc[c]);
+        }
+      uint4 q;
+      q.x = pack2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), is_bf16);
+      q.y = pack2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), is_bf16);
+      q.z = pack2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), is_bf16);
+      q.w = pack2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), is_bf16);
+      o[x] = q;
+    }
   }
 }
 
@@ -609,7 +614,7 @@ int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int
   const int bf = mode == SPN_MODE_BF16 ? 1 : 0;
   {
     SpnProfScope prof(ctx, SPN_L_BLOCK1, s);
-    dim3 g(spn_cdiv(W, 32 * kC1Px), H, B);
+    dim3 g(spn_cdiv(W, 32 * kC1Px), spn_cdiv(H, kC1Rows), B);
     conv1_c8_kernel<<<g, 256, 0, s>>>(d_images, st->w1, ctx->layers[0].bias, A, B, H, W, bf);
     SPN_CHECK_LAUNCH(ctx);
   }

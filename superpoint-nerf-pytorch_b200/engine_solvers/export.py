@@ -11,7 +11,7 @@ whose result export.py:69 discards is not computed.
 
 Extension keys under ``homography_adaptation`` (optional): ``sampler`` 'device' (default, spn_sample_homographies)
 or 'numpy' (the reference's host sampler and RNG order), ``seed``, ``images_per_launch`` (default 1),
-``max_forwards`` (forwards per encoder launch, default 128).
+``max_forwards`` (forwards per encoder launch, default 128), ``streams`` (concurrent CUDA streams, default 1).
 """
 import os
 from pathlib import Path
@@ -42,6 +42,8 @@ class HomographyAdaptation:
         self.sampler = Homographic_aug(self.ha, device)
         self.max_forwards = int(self.ha.get("max_forwards", 128))
         self.seed = int(self.ha.get("seed", 0))
+        self.n_streams = max(1, int(self.ha.get("streams", 1)))
+        self._streams = None
         if not self.ha["valid_border_margin"]:
             # the reference's margin-0 path is shape-broken (mask stays 4-D)
             raise ValueError("homography_adaptation.valid_border_margin must be >= 1")
@@ -55,15 +57,42 @@ class HomographyAdaptation:
 
     @torch.no_grad()
     def heatmaps(self, images, homographies=None, enable_HA=True, first_index=0):
-        """images (NI,1,H,W) CUDA fp32 -> (aggregated heatmap (NI,H,W), homographies used (NI,n_h,3,3) or None)."""
+        """images (NI,1,H,W) CUDA fp32 -> (aggregated heatmap (NI,H,W), homographies used (NI,n_h,3,3) or None).
+        With ``streams`` > 1 the images are split into groups that run on separate CUDA streams (each with its own
+        context/workspace) so the bandwidth-bound kernels of one group overlap the tensor-core kernels of another."""
+        NI = images.shape[0]
+        n_h = int(self.ha["num"]) - 1
+        if self.n_streams == 1 or NI < 2 or not enable_HA or n_h == 0:
+            return self._heatmaps_group(images, homographies, enable_HA, first_index, 0)
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=images.device) for _ in range(self.n_streams)]
+        cur = torch.cuda.current_stream(images.device)
+        groups = [g for g in torch.chunk(torch.arange(NI), self.n_streams) if len(g)]
+        heats, hs = [], []
+        for k, idx in enumerate(groups):
+            st = self._streams[k]
+            st.wait_stream(cur)
+            lo, hi = int(idx[0]), int(idx[-1]) + 1
+            with torch.cuda.stream(st):
+                hg = None if homographies is None else homographies[lo:hi]
+                heat, h = self._heatmaps_group(images[lo:hi], hg, enable_HA, first_index + lo, k)
+            heat.record_stream(cur)
+            h.record_stream(cur)
+            heats.append(heat)
+            hs.append(h)
+        for k in range(len(groups)):
+            cur.wait_stream(self._streams[k])
+        return torch.cat(heats), torch.cat(hs)
+
+    def _heatmaps_group(self, images, homographies, enable_HA, first_index, slot):
         NI, _, H, W = images.shape
-        ctx = self.model.native()
+        ctx = self.model.native(slot)
         imgs = images.detach().to(torch.float32).contiguous().view(NI, H, W)
         if not enable_HA:
-            return self.model.prob_heatmap(imgs), None
+            return self.model.prob_heatmap(imgs, slot=slot), None
         n_h = int(self.ha["num"]) - 1
         if n_h == 0:
-            return self.model.prob_heatmap(imgs), None
+            return self.model.prob_heatmap(imgs, slot=slot), None
         if homographies is None:
             homographies = self._homographies(NI, n_h, H, W, first_index)
         h = homographies.to(self.device, torch.float32).contiguous().view(NI, n_h, 3, 3)
@@ -73,7 +102,7 @@ class HomographyAdaptation:
         probs = torch.empty((B, H, W), dtype=torch.float32, device=imgs.device)
         for s in range(0, B, self.max_forwards):                                 # export.py:69-70
             e = min(B, s + self.max_forwards)
-            self.model.prob_heatmap(warped[s:e], mask=mask[s:e], out=probs[s:e])
+            self.model.prob_heatmap(warped[s:e], mask=mask[s:e], out=probs[s:e], slot=slot)
         agg = ctx.ha_aggregate(probs.view(NI, n_h + 1, H, W), h, self.ha["valid_border_margin"],
                                self.ha["aggregation"])                           # export.py:72-77,106-114
         return agg, h

@@ -67,28 +67,32 @@ class SuperPoint(nn.Module):
         if prec not in MODES:
             raise ValueError(f"precision must be one of {sorted(MODES)}, got {prec!r}")
         self.mode = MODES[prec]
-        self._ctx = None
-        self._packed_key = None
+        self._ctxs = {}        # slot -> Context (slot 0 is the default; extra slots serve concurrent streams)
+        self._packed_keys = {}
 
     # ---- native state ----------------------------------------------------------------------------
     def _weights_key(self):
         return tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict(keep_vars=True).items())
 
-    def native(self) -> Context:
-        """The Context holding this model's packed weights (re-packed when parameters change)."""
+    def native(self, slot: int = 0) -> Context:
+        """The Context holding this model's packed weights (re-packed when parameters change).  Each ``slot`` is an
+        independent context (own workspace), so different slots can run concurrently on different CUDA streams."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise NativeError("SuperPoint (b200) runs on CUDA only: move the model with .to('cuda') (no CPU fallback)")
-        if self._ctx is None or self._ctx.device != (dev.index or 0):
-            with torch.cuda.device(dev):
-                self._ctx = Context(dev.index or 0)
-            self._packed_key = None
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        ctx = self._ctxs.get(slot)
+        if ctx is None or ctx.device != idx:
+            with torch.cuda.device(idx):
+                ctx = Context(idx)
+            self._ctxs[slot] = ctx
+            self._packed_keys[slot] = None
         key = self._weights_key()
-        if key != self._packed_key:
-            with torch.cuda.device(dev):
-                self._ctx.load_state_dict(self.state_dict())
-            self._packed_key = key
-        return self._ctx
+        if key != self._packed_keys.get(slot):
+            with torch.cuda.device(idx):
+                ctx.load_state_dict(self.state_dict())
+            self._packed_keys[slot] = key
+        return ctx
 
     def train(self, mode=True):
         if mode:
@@ -127,10 +131,10 @@ class SuperPoint(nn.Module):
         return out
 
     @torch.no_grad()
-    def prob_heatmap(self, images, mask=None, out=None):
+    def prob_heatmap(self, images, mask=None, out=None, slot=0):
         """images (B,H,W) fp32 CUDA -> prob_heatmap (B,H,W), optionally multiplied by a u8 mask (export.py:69-70).
         Skips everything ExportDetections.step discards (logits copy, in-model NMS)."""
-        ctx = self.native()
+        ctx = self.native(slot)
         B, H, W = images.shape
         with torch.cuda.device(images.device):
             ctx.encoder_forward(images, self.mode)
