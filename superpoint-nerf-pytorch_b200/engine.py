@@ -1,0 +1,123 @@
+"""CLI with the reference's task names and flags (engine.py:43-208), export tasks only.
+
+    python -m superpoint_nerf_pytorch_b200.engine --config_path configs/magicpoint_coco_export.yaml \
+        --task export_pseudo_labels [--pseudo_labels.split training] [--pseudo_labels.enable_Homography_Adaptation True]
+
+Same YAML schema as the reference (``data``, ``homography_adaptation``, ``model``, ``pretrained``).  What differs:
+  * ``model.script`` / ``model.class_name`` resolve inside this package (models/SuperPoint.py), so an unmodified
+    reference config selects the B200 implementation;
+  * the data loaders (COCO / HPatches image decoding) are out of scope: if the reference
+    package is importable its ``get_loader`` is used, otherwise ``--synthetic N`` feeds N synthetic images of the
+    configured size;
+  * ``train`` and ``export_NeRF_labels`` are out of scope and rejected.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Literal
+
+import torch
+import tyro
+import yaml
+
+from . import settings
+from .engine_solvers.export import Export_Hpatches_Descriptors, Export_Hpatches_Repeatability, ExportDetections
+from .utils.get_model import get_model
+from .utils.sharding import shard_indices
+
+
+@dataclass
+class export_pseudo_labels_split:
+    """Export pseudo labels on train, validation or test split.
+
+    Args:
+        enable_Homography_Adaptation: Enable homography adaptation during export.
+        split: The split to export pseudo labels on.
+    """
+    enable_Homography_Adaptation: bool = True
+    split: Literal["training", "validation", "test"] = "training"
+
+
+class SyntheticLoader:
+    """Stand-in for the reference loaders: yields the batch dictionaries the export tasks consume."""
+
+    def __init__(self, n, shape, task, rank=0, world=1, seed=0):
+        self.ids = list(shard_indices(n, rank, world))
+        self.shape, self.task, self.seed = tuple(shape), task, seed
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __iter__(self):
+        for i in self.ids:
+            g = torch.Generator().manual_seed(self.seed + i)
+            img = torch.rand((1, 1, *self.shape), generator=g)
+            if self.task == "export_pseudo_labels":
+                yield {"raw": {"image": img}, "name": [f"synthetic_{i:08d}"]}
+            else:
+                h = torch.eye(3).unsqueeze(0)
+                h[0, 0, 2], h[0, 1, 2] = 4.0, -3.0
+                yield {"image": img, "warped_image": torch.roll(img, shifts=(-3, 4), dims=(2, 3)), "homography": h,
+                       "name": [f"synthetic_{i:08d}"]}
+
+
+def load_pretrained(model, config, device):
+    """engine.py:108-117: copy the keys present in both dicts, then load_state_dict."""
+    state = model.state_dict()
+    ckpt = torch.load(Path(settings.CKPT_PATH, config["pretrained"]), map_location=device)
+    for k, v in ckpt["model_state_dict"].items():
+        if k in state:
+            state[k] = v
+    model.load_state_dict(state)
+    print("\033[92m✅ Loaded pretrained model \033[0m")
+
+
+@tyro.conf.configure(tyro.conf.FlagConversionOff)
+def main(config_path: str,
+         task: Literal["export_pseudo_labels", "export_HPatches_Repeatability", "export_HPatches_Descriptors",
+                       "train", "export_NeRF_labels"],
+         pseudo_labels: export_pseudo_labels_split = export_pseudo_labels_split(),
+         synthetic: int = 0, random_init: bool = False) -> None:
+    """Run one export task.
+
+    Args:
+        config_path: Path to configuration.
+        task: The task to be performed.
+        synthetic: feed this many synthetic images instead of the dataset loader.
+        random_init: skip loading `pretrained` (benchmarking with random-init weights).
+    """
+    if task in ("train", "export_NeRF_labels"):
+        raise SystemExit(f"task {task!r} is outside the B200 hot path (SURVEY.md section 8); use the reference for it")
+    with open(config_path, "r") as f:
+        config = yaml.safe_load(f)
+    if not torch.cuda.is_available():
+        raise SystemExit("CUDA is not available: this implementation has no CPU fallback")
+    rank, world = 0, 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    device = f"cuda:{torch.cuda.current_device()}"
+    model = get_model(config["model"], device=device)
+    if not random_init:
+        assert config["pretrained"], "Use pretrained model to export."
+        load_pretrained(model, config, device)
+    if synthetic:
+        loader = SyntheticLoader(synthetic, config["data"]["preprocessing"]["resize"], task, rank, world)
+    else:
+        try:
+            from superpoint.utils.data_loaders import get_loader  # the reference's loaders, if installed
+        except ImportError as e:
+            raise SystemExit("dataset loaders are out of scope here: install the reference package for COCO/HPatches "
+                             f"loading or pass --synthetic N ({e})")
+        loader = get_loader(config, task, device="cpu", export_split=pseudo_labels.split) if task == "export_pseudo_labels" \
+            else get_loader(config, task, device="cpu")
+    if task == "export_pseudo_labels":
+        ExportDetections(config, model, loader, pseudo_labels.split, pseudo_labels.enable_Homography_Adaptation, device)
+    elif task == "export_HPatches_Repeatability":
+        Export_Hpatches_Repeatability(config, model, loader, device)
+    else:
+        Export_Hpatches_Descriptors(config, model, loader, device)
+
+
+if __name__ == "__main__":
+    tyro.cli(main, use_underscores=True)
