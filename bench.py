@@ -50,6 +50,17 @@ FLOPS_PER_IMAGE = 1.2161e12
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+def ncu_block2_traffic_per_forward():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the block_2 launch in the committed `ncu --set full` capture
+    (profiles/r1_kernels.json, 100 forwards per launch) -> bytes per forward, or None."""
+    try:
+        ks = json.loads((ROOT / "profiles" / "r1_kernels.json").read_text())
+        k = max((k for k in ks if "conv_tc_kernel<9>" in k["kernel"]), key=lambda k: k["time_us"])
+        return (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6 / 100.0
+    except Exception:
+        return None
+
+
 def peaks():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -206,12 +217,14 @@ def run_native(args):
         return float(t.item())
 
     # ---- device-resident throughput -----------------------------------------------------------------------------
-    for i in range(args.warmup):
-        device_step(i)
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for i in range(args.warmup):
+        device_step(i)
+    barrier()
+    if sampler:
+        sampler.rows.clear()   # keep only samples taken during the timed region
     ctxs = list(model._ctxs.values())     # one context per concurrent stream
 
     def prof_read_all():
@@ -296,8 +309,12 @@ def run_native(args):
     total_kernel_ms = sum(t for t, _ in prof.values())
     roof = None
     if dom:
+        tpf = ncu_block2_traffic_per_forward() if args.precision != "fp32" else None
+        fwd_per_launch = forwards / max(dom["launches"], 1)
         roof = {"bound": "tensor", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"],
-                "traffic": None, "kernel": "backbone.block_2 3x3 conv 64->64 @240x320 (implicit GEMM M=pixels N=64 K=576)",
+                "traffic": (tpf * fwd_per_launch) if tpf else None, "traffic_unit": "bytes per launch (ncu dram read+write)",
+                "algorithmic_flops_per_launch": LAYER_FLOPS["backbone.block_2"] * fwd_per_launch,
+                "ms_per_launch": dom["ms_per_launch"], "kernel": "backbone.block_2 3x3 conv 64->64 @240x320 (implicit GEMM M=pixels N=64 K=576)",
                 "peak_source": f"{pk_kind} bf16_tflops_sustained", "share_of_step": (prof["backbone.block_2"][0] / total_kernel_ms)
                 if total_kernel_ms else None}
     line = {"metric": "pseudo-label img/s (240x320, 100 H)", "value": value, "unit": "img/s", "n_gpus": world,
@@ -325,11 +342,13 @@ def run_native(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SPN_B200_PRECISION", "fp32"), choices=["fp32", "f16", "bf16"])
-    ap.add_argument("--images-per-step", type=int, default=4)
+    ap.add_argument("--precision", default=os.environ.get("SPN_B200_PRECISION", "f16"), choices=["fp32", "f16", "bf16"],
+                    help="f16 (default): tcgen05 convolutions, fp16 operands / fp32 accumulate, 5e-3 parity gate; "
+                         "fp32: strict FFMA convolutions, 1e-4 parity gate")
+    ap.add_argument("--images-per-step", type=int, default=16)
     ap.add_argument("--max-forwards", type=int, default=100)
     ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--ref-homographies", type=int, default=6, help="homographies in the bounded CPU sample")
