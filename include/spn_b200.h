@@ -78,6 +78,14 @@ SPN_API int spn_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_in,
  * (H, W multiples of 8). */
 SPN_API int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode, spn_stream stream);
 
+/* Fused K.warp_perspective(image, H) (export.py:51) + VGG_BACKBONE.forward for the homography-adaptation slots
+ * slot = i*(n_h+1) + j (j == 0: image i itself, j >= 1: image i warped by homography j-1) with
+ * slot_begin <= slot < slot_begin + n_slots; tensor-core modes only.  The warped images are never written to memory:
+ * the warp is evaluated inside the first convolution kernel.  d_images [n_images][H][W], d_hinv [n_images][n_h][9]
+ * (pixel-space inverses, as for spn_warp_batch).  Leaves the feature map of the n_slots forwards inside ctx. */
+SPN_API int spn_encoder_forward_ha(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h,
+                                   int slot_begin, int n_slots, int H, int W, int mode, spn_stream stream);
+
 /* Detector_head.forward up to prob_heatmap (heads.py:17-28): convPa, convPb, softmax(65), drop dustbin,
  * pixel_shuffle(8).  d_mask (nullable) [B][H][W] u8 multiplies the heatmap (export.py:70).
  * d_logits (nullable) [B][65][H/8][W/8]; d_prob [B][H][W]. */
@@ -116,7 +124,7 @@ SPN_API int spn_nms_stats(spn_ctx* ctx, int B, int H, int W, int64_t* h_out);
  *   slot = i*(n_h+1)         : the image itself, mask = 1 (identity forward, export.py:93)
  * d_hinv [n_images][n_h][9] fp32 are the pixel-space INVERSES of the matrices the reference passes
  * (kornia samples src at M^-1 p).  d_images [n_images][H][W]; d_warped [n_images*(n_h+1)][H][W] fp32;
- * d_mask same shape u8. */
+ * d_mask same shape u8.  d_warped may be NULL (mask only: the fused encoder spn_encoder_forward_ha warps on the fly). */
 SPN_API int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H, int W,
                    int margin, float* d_warped, uint8_t* d_mask, spn_stream stream);
 

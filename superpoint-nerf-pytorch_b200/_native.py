@@ -43,6 +43,7 @@ PROTOTYPES = {
     "spn_pack_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
     "spn_conv_layer": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "spn_encoder_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "spn_encoder_forward_ha": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "spn_detector_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "spn_descriptor_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "spn_dense_descriptors": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
@@ -180,6 +181,17 @@ class Context:
         B, H, W = images.shape
         self._call("spn_encoder_forward", self.handle, _ptr(images), B, H, W, mode, _stream())
 
+    def encoder_forward_ha(self, images: torch.Tensor, hinv, slot_begin: int, n_slots: int, mode: int):
+        """Fused warp + encoder for slots [slot_begin, slot_begin+n_slots) of (images (NI,H,W), hinv (NI,n_h,3,3))."""
+        images, hinv = _dense(images), _dense(hinv)
+        _chk_dev(images, torch.float32, "images")
+        NI, H, W = images.shape
+        n_h = 0 if hinv is None else hinv.shape[1]
+        if n_h:
+            _chk_dev(hinv, torch.float32, "hinv")
+        self._call("spn_encoder_forward_ha", self.handle, _ptr(images), NI, _ptr(hinv) if n_h else None, n_h, int(slot_begin),
+                   int(n_slots), H, W, mode, _stream())
+
     def detector_head_forward(self, B, H, W, mode, mask=None, want_logits=False, out=None):
         dev = torch.device("cuda", self.device)
         if out is None:
@@ -244,15 +256,15 @@ class Context:
         return {"global_rounds": int(out[0]), "local_iterations": int(out[1]), "tile_visits": int(out[2])}
 
     # ---- homography adaptation -------------------------------------------------------------------
-    def warp_batch(self, images, hinv, margin):
-        """images (NI,H,W), hinv (NI,n_h,3,3) -> warped (NI*(n_h+1),H,W) fp32, mask u8 (same shape)."""
+    def warp_batch(self, images, hinv, margin, want_warped=True):
+        """images (NI,H,W), hinv (NI,n_h,3,3) -> warped (NI*(n_h+1),H,W) fp32 (None if not wanted), mask u8 (same shape)."""
         images, hinv = _dense(images), _dense(hinv)
         _chk_dev(images, torch.float32, "images")
         NI, H, W = images.shape
         n_h = 0 if hinv is None else hinv.shape[1]
         if n_h:
             _chk_dev(hinv, torch.float32, "hinv")
-        warped = torch.empty((NI * (n_h + 1), H, W), dtype=torch.float32, device=images.device)
+        warped = torch.empty((NI * (n_h + 1), H, W), dtype=torch.float32, device=images.device) if want_warped else None
         mask = torch.empty((NI * (n_h + 1), H, W), dtype=torch.uint8, device=images.device)
         self._call("spn_warp_batch", self.handle, _ptr(images), NI, _ptr(hinv) if n_h else None, n_h, H, W, int(margin),
                    _ptr(warped), _ptr(mask), _stream())

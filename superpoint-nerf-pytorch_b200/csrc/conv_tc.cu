@@ -25,8 +25,11 @@
 #include <vector>
 
 #include "spn_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
+
+using namespace tcptx;
 
 constexpr int kTW = 8, kTH = 16;              // output tile: 8 x 16 pixels = 128 GEMM rows
 constexpr int kThreads = 192;
@@ -51,118 +54,6 @@ struct TcParams {
   const float* bias;      // [cout_slices * 64]
   const void* wimg;       // [cout_slices][cin_blocks][taps][4][2][64][8] halfs
 };
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  while (!ok) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(pred));
-  return pred;
-}
-// same instruction, descriptors given as (lo, hi) words so that only `lo` changes between the MMAs of a tile
-__device__ __forceinline__ void umma_f16_2w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                            uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// SWIZZLE_NONE K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {
-  if (is_bf16) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&t);
-  }
-  __half2 t = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int is_bf16) {
-  if (is_bf16) {
-    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-    return *reinterpret_cast<uint32_t*>(&r);
-  }
-  __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
-}
 
 // ------------------------------------------------------------------------------------------------ main kernel
 template <int TAPS>
@@ -451,6 +342,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct TcState {
   EncodeTiledFn encode = nullptr;
   float* w1 = nullptr;      // block_1 weights [9][64] fp32 (BN folded)
+  void* w1img[2] = {nullptr, nullptr};  // block_1 as tcgen05 operand B: [chunk 2][cout 64][8] (K = 9 taps padded to 16)
   float* bias_pad[SPN_NUM_LAYERS] = {};  // [cout_slices*64]
   bool smem_attr_set = false;
 };
@@ -571,6 +463,24 @@ int spn_tc_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float
       for (int t = 0; t < 9; ++t) w[t * 64 + co] = h_wfold[(size_t)co * 9 + t];
     if (!st->w1) SPN_CUDA(cudaMalloc((void**)&st->w1, w.size() * sizeof(float)));
     SPN_CUDA(cudaMemcpy(st->w1, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    for (int bf = 0; bf < 2; ++bf) {
+      // K = 16: k 0..8 = the nine taps, k 9 / 10 = the bias as a (hi, lo) pair of 16-bit values multiplied by the
+      // constant-one columns the front end puts into A1 (so block_1's epilogue needs no bias add)
+      std::vector<uint16_t> img(2 * 64 * 8, 0);
+      auto from16 = [&](uint16_t h) {
+        if (bf) { __nv_bfloat16 v = *reinterpret_cast<__nv_bfloat16*>(&h); return __bfloat162float(v); }
+        __half v = *reinterpret_cast<__half*>(&h);
+        return __half2float(v);
+      };
+      for (int co = 0; co < 64; ++co) {
+        for (int t = 0; t < 9; ++t) img[((size_t)(t / 8) * 64 + co) * 8 + (t % 8)] = to16(h_wfold[(size_t)co * 9 + t], bf);
+        const uint16_t hi = to16(h_bfold[co], bf);
+        img[((size_t)1 * 64 + co) * 8 + 1] = hi;
+        img[((size_t)1 * 64 + co) * 8 + 2] = to16(h_bfold[co] - from16(hi), bf);
+      }
+      if (!st->w1img[bf]) SPN_CUDA(cudaMalloc(&st->w1img[bf], img.size() * 2));
+      SPN_CUDA(cudaMemcpy(st->w1img[bf], img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+    }
     return SPN_OK;
   }
   if (L.cin % 64 != 0) return SPN_OK;  // not a tensor-core layer
@@ -602,9 +512,15 @@ int spn_tc_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float
   return SPN_OK;
 }
 
-int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode, cudaStream_t s) {
+const float* spn_tc_bias(spn_ctx* ctx, int layer) { return tc_state(ctx)->bias_pad[layer]; }
+
+// Encoder over `n_slots` forwards.  d_hinv == nullptr: slot i is image i (plain forward).  Otherwise slot =
+// src*(n_h+1)+j is image `src` warped by homography j-1 (j == 0: the image itself) and the warp is fused in.
+int spn_tc_encoder_slots(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots,
+                         int H, int W, int mode, cudaStream_t s) {
   TcState* st = tc_state(ctx);
   if (!st->w1) { spn_set_error("block_1 has no weights"); return SPN_E_STATE; }
+  const int B = n_slots;
   const TcPlan pl = tc_plan(B, H, W);
   int rc = spn_ensure_ws(ctx, pl.total, s);
   if (rc) return rc;
@@ -612,13 +528,20 @@ int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int
   char* Bq = A + pl.a;
   char* F = Bq + pl.b;
   const int bf = mode == SPN_MODE_BF16 ? 1 : 0;
-  {
-    SpnProfScope prof(ctx, SPN_L_BLOCK1, s);
-    dim3 g(spn_cdiv(W, 32 * kC1Px), spn_cdiv(H, kC1Rows), B);
-    conv1_c8_kernel<<<g, 256, 0, s>>>(d_images, st->w1, ctx->layers[0].bias, A, B, H, W, bf);
-    SPN_CHECK_LAUNCH(ctx);
+  const char* nofuse = getenv("SPN_TC_NOFUSE");
+  if (nofuse && atoi(nofuse)) {
+    SPN_REQUIRE(!d_hinv, "SPN_TC_NOFUSE: the unfused path takes already-warped images");
+    {
+      SpnProfScope prof(ctx, SPN_L_BLOCK1, s);
+      dim3 g(spn_cdiv(W, 32 * kC1Px), spn_cdiv(H, kC1Rows), B);
+      conv1_c8_kernel<<<g, 256, 0, s>>>(d_images + (size_t)slot_begin * H * W, st->w1, ctx->layers[0].bias, A, B, H, W, bf);
+      SPN_CHECK_LAUNCH(ctx);
+    }
+    if ((rc = launch_conv_tc(ctx, 1, mode, A, Bq, B, H, W, true, true, 0, s))) return rc;
+  } else {
+    // warp + block_1 + block_2 in one kernel (front_tc.cu): block_1's output never reaches HBM
+    if ((rc = spn_front_tc_launch(ctx, d_images, d_hinv, n_h, slot_begin, n_slots, H, W, mode, st->w1img[bf], Bq, s))) return rc;
   }
-  if ((rc = launch_conv_tc(ctx, 1, mode, A, Bq, B, H, W, true, true, 0, s))) return rc;
   if ((rc = launch_conv_tc(ctx, 2, mode, Bq, A, B, H / 2, W / 2, true, false, 0, s))) return rc;
   if ((rc = launch_conv_tc(ctx, 3, mode, A, Bq, B, H / 2, W / 2, true, true, 0, s))) return rc;
   if ((rc = launch_conv_tc(ctx, 4, mode, Bq, A, B, H / 4, W / 4, true, false, 0, s))) return rc;
@@ -627,6 +550,10 @@ int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int
   if ((rc = launch_conv_tc(ctx, 7, mode, A, F, B, H / 8, W / 8, true, false, 0, s))) return rc;
   ctx->feat = F;
   return SPN_OK;
+}
+
+int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode, cudaStream_t s) {
+  return spn_tc_encoder_slots(ctx, d_images, nullptr, 0, 0, B, H, W, mode, s);
 }
 
 int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_logits, cudaStream_t s) {
@@ -679,6 +606,7 @@ void spn_tc_destroy(spn_ctx* ctx) {
   TcState* st = (TcState*)ctx->tc;
   if (!st) return;
   if (st->w1) cudaFree(st->w1);
+  for (auto& w : st->w1img) if (w) cudaFree(w);
   for (auto& b : st->bias_pad) if (b) cudaFree(b);
   delete st;
   ctx->tc = nullptr;

@@ -1,0 +1,342 @@
+// Fused front end of the fast path: homography warp -> block_1 (3x3, 1->64) -> block_2 (3x3, 64->64, ReLU, 2x2 pool)
+// in ONE tcgen05 kernel.  Neither the warped image (614 KB / homography) nor block_1's output (9.8 MB / forward, the
+// largest tensor of the network) ever reaches HBM: the kernel reads the fp32 source image through L2 and writes
+// block_2's pooled C8 output (2.5 MB / forward).
+//
+// Reference semantics fused here: K.warp_perspective(image, H, bilinear) (engine_solvers/export.py:51) +
+// VGG_Block 1 and 2 (models/model_utils/VGG_Backbone.py:23-36, 60-63).
+//
+// Per CTA tile (8 x 16 output pixels of block_2 before pooling = M 128), pipelined over tiles by warp role:
+//   P  warps 10-13  bilinear-sample the 12 x 20 warped-image patch, build block_1's im2col operand A1
+//                   (256 rows = the 10 x 18 halo pixels (180 used), K = 9 taps padded to 16, fp16) in SMEM
+//   M  warp 1       MMA1: D1 = A1 . W1 (2 x M128 N64 K16) into TMEM, issued one tile AHEAD of
+//                   MMA2: D2 += slab(tap) . W2(tap) (36 x M128 N64 K16, weights resident in SMEM)
+//   E1 warps 6-9    D1 (bias already added through A1's ones columns, rows outside the image exactly 0 = block_2's
+//                   zero padding) -> ReLU -> fp16 -> the slab
+//                   [chunk][halo row][halo col][8] that MMA2's nine shifted descriptors read
+//   E2 warps 2-5    D2 -> +bias2 -> ReLU -> 2x2 max-pool (two shfl.xor) -> 16-byte C8 stores
+//   warp 0          weight loader (cp.async.bulk)
+// All hand-offs are mbarriers (generic-proxy SMEM writes are published to the tensor core with fence.proxy.async).
+#include "spn_common.cuh"
+#include "spn_geom.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+using namespace tcptx;
+using namespace spngeom;
+
+constexpr int kTW = 8, kTH = 16;
+constexpr int kPW = kTW + 2, kPH = kTH + 2;          // block_1 halo tile: 10 x 18 = 180 pixels
+constexpr int kHalo = kPW * kPH;
+constexpr int kQW = kTW + 4, kQH = kTH + 4;          // warped-image patch: 12 x 20 = 240 pixels
+constexpr uint32_t kChStride = (uint32_t)kHalo * 16;  // slab bytes between 8-channel groups (2880)
+constexpr int kSlabBytes = 8 * kHalo * 16;            // 23040
+constexpr int kStageBytes = (kSlabBytes + 1023) & ~1023;
+constexpr int kW2Bytes = 9 * 8192;                    // block_2 weights, one 64-channel slice
+constexpr int kW1Bytes = 2 * 64 * 16;                 // block_1 weights as operand B: [chunk 2][cout 64][8]
+constexpr int kA1Rows = 256;
+constexpr int kA1Bytes = 2 * kA1Rows * 16;            // [chunk 2][row 256][8 halfs]
+constexpr int kStages = 4;
+constexpr int kThreads = 448;                         // 14 warps
+
+struct FrontParams {
+  const float* images;   // [n_src][H][W] fp32
+  const float* hinv;     // [n_src][n_h][9] or null (plain forward: slot == source image)
+  int n_h;               // homographies per source image (slot = src * (n_h + 1) + j, j == 0 is the identity)
+  int slot_begin, n_slots;
+  int H, W, tiles_x, tiles_y;
+  int is_bf16;
+  const void* w1img;     // operand-B image of block_1
+  const float* bias1;    // [64]
+  const void* w2img;     // operand-B image of block_2 (72 KB)
+  const float* bias2;    // [64]
+  void* out;             // C8 [n_slots][8][H/2][W/2][8]
+};
+
+__device__ __forceinline__ uint16_t to16(float v, int bf) {
+  if (bf) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a1_full[2], bar_a1_empty[2], bar_d1_full[2], bar_d1_empty[2],
+      bar_slab_full[kStages], bar_slab_empty[kStages], bar_d2_full[2], bar_d2_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias2_s[64];
+  __shared__ __align__(16) uint16_t patch_s[2][kQH * kQW];
+  __shared__ float hm_s[2][12];
+
+  uint8_t* w2s = smem;                                  // 73728
+  uint8_t* w1s = smem + kW2Bytes;                       // 2048
+  uint8_t* a1s = w1s + kW1Bytes;                        // 2 x 8192
+  uint8_t* slab0 = a1s + 2 * kA1Bytes;                  // kStages x 23552  (1024-aligned: 73728+2048+16384 = 92160)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int n_tiles = p.n_slots * tiles_per_img;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_w, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_a1_full[i], 128); mbar_init(&bar_a1_empty[i], 1);
+      mbar_init(&bar_d1_full[i], 1);   mbar_init(&bar_d1_empty[i], 128);
+      mbar_init(&bar_d2_full[i], 1);   mbar_init(&bar_d2_empty[i], 128);
+    }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bar_slab_full[i], 128); mbar_init(&bar_slab_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 64) bias2_s[threadIdx.x] = p.bias2[threadIdx.x];
+  // A1 rows >= 180 are never written again: zero both buffers once
+  for (int i = threadIdx.x; i < 2 * kA1Bytes / 16; i += kThreads) reinterpret_cast<uint4*>(a1s)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 1) {  // TMEM: D2 2 x 64 columns, D1 2 buffers x 2 halves x 64 columns -> 384, allocate 512
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zero fill above is read by the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t fmt = p.is_bf16 ? 1u : 0u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+  if (warp == 0) {
+    // ===================== weight loader =====================
+    if (elect_one()) {
+      mbar_expect_tx(&bar_w, (uint32_t)(kW2Bytes + kW1Bytes));
+      for (int o = 0; o < kW2Bytes; o += 8192) bulk_load(w2s + o, (const uint8_t*)p.w2img + o, 8192, &bar_w);
+      bulk_load(w1s, p.w1img, kW1Bytes, &bar_w);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    mbar_wait(&bar_w, 0);
+    const uint32_t hi_a1 = (128u >> 4) | (1u << 14);                  // SBO 128 B (8 rows x 16 B), version 1
+    const uint32_t lo_a1_c = ((uint32_t)(kA1Rows * 16) >> 4) << 16;   // LBO 4096 B between the two K chunks
+    const uint32_t hi_b = (128u >> 4) | (1u << 14);
+    const uint32_t lo_b_c = (1024u >> 4) << 16;
+    const uint32_t hi_a2 = ((uint32_t)(kPW * 16) >> 4) | (1u << 14);  // SBO = one halo row (160 B)
+    const uint32_t lo_a2_c = (kChStride >> 4) << 16;
+    const uint32_t w1_lo = (smem_u32(w1s) >> 4) | lo_b_c, w2_lo = (smem_u32(w2s) >> 4) | lo_b_c;
+    const uint32_t a1_addr = smem_u32(a1s), slab_addr = smem_u32(slab0);
+    const uint32_t d1_col = tmem_base + 128;
+
+    auto issue_mma1 = [&](int i) {  // block_1 for local tile i: D1[b][h] = A1[b] rows h*128.. times W1
+      const int b = i & 1;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      mbar_wait(&bar_a1_full[b], ph);
+      mbar_wait(&bar_d1_empty[b], ph ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t a_lo = ((a1_addr + (uint32_t)b * kA1Bytes + (uint32_t)h * 128 * 16) >> 4) | lo_a1_c;
+          umma_f16_2w(d1_col + (uint32_t)(b * 2 + h) * 64, a_lo, hi_a1, w1_lo, hi_b, idesc, 0u);
+        }
+        umma_commit(&bar_a1_empty[b]);
+        umma_commit(&bar_d1_full[b]);
+      }
+      __syncwarp();
+    };
+
+    int i = 0;
+    if ((int)blockIdx.x < n_tiles) issue_mma1(0);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      if (t + (int)gridDim.x < n_tiles) issue_mma1(i + 1);  // one tile ahead, so E1 overlaps MMA2 of this tile
+      const int stage = i % kStages, acc = i & 1;
+      const uint32_t sph = (uint32_t)(i / kStages) & 1u, aph = (uint32_t)(i >> 1) & 1u;
+      mbar_wait(&bar_slab_full[stage], sph);
+      mbar_wait(&bar_d2_empty[acc], aph ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = ((slab_addr + (uint32_t)stage * kStageBytes) >> 4) | lo_a2_c;
+        const uint32_t d2 = tmem_base + (uint32_t)acc * 64;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap % 3;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t aoff = ((uint32_t)(ky * kPW + kx) * 16 + (uint32_t)kk * 2 * kChStride) >> 4;
+            const uint32_t boff = ((uint32_t)tap * 8192 + (uint32_t)kk * 2048) >> 4;
+            umma_f16_2w(d2, a_lo + aoff, hi_a2, w2_lo + boff, hi_b, idesc, (tap | kk) ? 1u : 0u);
+          }
+        }
+        umma_commit(&bar_slab_empty[stage]);
+        umma_commit(&bar_d2_full[acc]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 10) {
+    // ===================== P: warped patch + im2col operand of block_1 =====================
+    const int pt = threadIdx.x - 320;  // 0..127
+    int i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int b = i & 1;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const int ls = t / tiles_per_img, rr = t - ls * tiles_per_img;
+      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      const int slot = p.slot_begin + ls;
+      const int src = p.hinv ? slot / (p.n_h + 1) : slot;
+      const int j = p.hinv ? slot - src * (p.n_h + 1) : 0;
+      const float* img = p.images + (size_t)src * p.H * p.W;
+      mbar_wait(&bar_a1_empty[b], ph ^ 1u);  // MMA1 of tile i-2 has consumed A1[b] (and patch_s[b] long before)
+      if (j > 0 && pt < 9) hm_s[b][pt] = __ldg(&p.hinv[((size_t)src * p.n_h + (j - 1)) * 9 + pt]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // 1. the 12 x 20 patch of the warped image around the tile (zero outside the frame = block_1's padding)
+      for (int s = pt; s < kQH * kQW; s += 128) {
+        const int py = s / kQW, px = s - py * kQW;
+        const int y = ty * kTH - 2 + py, x = tx * kTW - 2 + px;
+        float v = 0.f;
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+          if (j == 0) {
+            v = __ldg(&img[(size_t)y * p.W + x]);
+          } else {
+            float sx, sy;
+            apply_h(hm_s[b], (float)x, (float)y, sx, sy);
+            v = bilinear_zero(img, sx, sy, p.H, p.W);
+          }
+        }
+        patch_s[b][s] = to16(v, p.is_bf16);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // 2. A1 row r = halo pixel (hy, hx): its 3x3 neighbourhood (K 0..8), then two constant-one columns that
+      //    multiply the (hi, lo) bias rows of W1.  Halo pixels outside the image get an all-zero row, so block_1's
+      //    output there is exactly 0 = block_2's zero padding.
+      const uint32_t one16 = p.is_bf16 ? 0x3F80u : 0x3C00u;
+      for (int r = pt; r < kHalo; r += 128) {
+        const int hy = r / kPW, hx = r - hy * kPW;
+        const int gy = ty * kTH - 1 + hy, gx = tx * kTW - 1 + hx;
+        uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
+        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+          const uint16_t* q = &patch_s[b][hy * kQW + hx];
+          c0.x = q[0] | ((uint32_t)q[1] << 16);
+          c0.y = q[2] | ((uint32_t)q[kQW] << 16);
+          c0.z = q[kQW + 1] | ((uint32_t)q[kQW + 2] << 16);
+          c0.w = q[2 * kQW] | ((uint32_t)q[2 * kQW + 1] << 16);
+          c1.x = q[2 * kQW + 2] | (one16 << 16);
+          c1.y = one16;
+        }
+        uint8_t* dst = a1s + (size_t)b * kA1Bytes + (size_t)r * 16;
+        *reinterpret_cast<uint4*>(dst) = c0;                    // taps 0..7
+        *reinterpret_cast<uint4*>(dst + kA1Rows * 16) = c1;     // tap 8, one, one, zero padding
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&bar_a1_full[b]);
+    }
+  } else if (warp >= 6) {
+    // ===================== E1: block_1 epilogue -> block_2's input slab =====================
+    const int q = warp & 3;
+    int i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int b = i & 1, stage = i % kStages;
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u, sph = (uint32_t)(i / kStages) & 1u;
+      mbar_wait(&bar_d1_full[b], ph);
+      mbar_wait(&bar_slab_empty[stage], sph ^ 1u);
+      tc_fence_after();
+      uint8_t* slab = slab0 + (size_t)stage * kStageBytes;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h * 128 + q * 32 >= kHalo) continue;  // warp-uniform: this lane quarter holds no halo pixel
+        const int r = h * 128 + q * 32 + lane;
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + 128 + (uint32_t)(b * 2 + h) * 64 + ((uint32_t)(q * 32) << 16);
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        if (r < kHalo) {  // bias is already inside D1 (ones columns of A1): ReLU + 16-bit pack + 8 x 16-byte stores
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c8 * 8 + 2 * e;
+              w[e] = max2(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), p.is_bf16), 0u, p.is_bf16);
+            }
+            *reinterpret_cast<uint4*>(slab + (size_t)c8 * kChStride + (size_t)r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_d1_empty[b]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&bar_slab_full[stage]);
+    }
+  } else {
+    // ===================== E2: block_2 epilogue (bias, ReLU, 2x2 max-pool, C8 store) =====================
+    const int q = warp & 3;
+    const int g = q * 4 + (lane >> 3), r = lane & 7;
+    const int Ho = p.H >> 1, Wo = p.W >> 1;
+    int i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int acc = i & 1;
+      const uint32_t aph = (uint32_t)(i >> 1) & 1u;
+      const int ls = t / tiles_per_img, rr = t - ls * tiles_per_img;
+      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      const int y = ty * kTH + g, x = tx * kTW + r;
+      mbar_wait(&bar_d2_full[acc], aph);
+      tc_fence_after();
+      uint32_t v[64];
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 64 + ((uint32_t)(q * 32) << 16);
+      tmem_ld32(taddr, v);
+      tmem_ld32(taddr + 32, v + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_d2_empty[acc]);
+      uint32_t h2[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float a = fmaxf(__uint_as_float(v[2 * c]) + bias2_s[2 * c], 0.f);
+        const float bb = fmaxf(__uint_as_float(v[2 * c + 1]) + bias2_s[2 * c + 1], 0.f);
+        h2[c] = pack2(a, bb, p.is_bf16);
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 1), p.is_bf16);
+        h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 8), p.is_bf16);
+      }
+      if (y < p.H && x < p.W && (g & 1) == 0 && (r & 1) == 0) {
+        uint4* o = reinterpret_cast<uint4*>(p.out);
+        const int oy = y >> 1, ox = x >> 1;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          o[(((size_t)ls * 8 + jj) * Ho + oy) * Wo + ox] = make_uint4(h2[4 * jj], h2[4 * jj + 1], h2[4 * jj + 2], h2[4 * jj + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace
+
+// d_out: C8 [n_slots][8][H/2][W/2][8]; weights of block_1 / block_2 from the context.
+int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots, int H,
+                        int W, int mode, const void* w1img, void* d_out, cudaStream_t s) {
+  const int bf = mode == SPN_MODE_BF16 ? 1 : 0;
+  const SpnLayer& L2 = ctx->layers[SPN_L_BLOCK2];
+  SPN_REQUIRE(L2.cin == 64 && L2.cout == 64 && L2.ks == 3 && L2.w16[bf], "front end needs block_2 = 3x3 conv 64->64 with packed weights");
+  FrontParams p;
+  memset(&p, 0, sizeof(p));
+  p.images = d_images; p.hinv = d_hinv; p.n_h = n_h; p.slot_begin = slot_begin; p.n_slots = n_slots;
+  p.H = H; p.W = W; p.tiles_x = spn_cdiv(W, kTW); p.tiles_y = spn_cdiv(H, kTH); p.is_bf16 = bf;
+  p.w1img = w1img; p.bias1 = ctx->layers[SPN_L_BLOCK1].bias; p.w2img = L2.w16[bf]; p.bias2 = spn_tc_bias(ctx, SPN_L_BLOCK2);
+  p.out = d_out;
+  const size_t dyn = (size_t)kW2Bytes + kW1Bytes + 2 * kA1Bytes + (size_t)kStages * kStageBytes + 1024;
+  SPN_CUDA(cudaFuncSetAttribute(front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  const long long tiles = (long long)n_slots * p.tiles_x * p.tiles_y;
+  const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  SpnProfScope prof(ctx, SPN_L_BLOCK2, s);
+  front_tc_kernel<<<grid, kThreads, dyn, s>>>(p);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}

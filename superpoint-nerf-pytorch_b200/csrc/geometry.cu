@@ -13,8 +13,11 @@
 #include <math.h>
 
 #include "spn_common.cuh"
+#include "spn_geom.cuh"
 
 namespace {
+
+using namespace spngeom;
 
 constexpr int kTileW = 32, kTileH = 8, kMaxKs = 16;
 constexpr int kRawH = kTileH + kMaxKs - 1, kRawW = kTileW + kMaxKs;  // 23 x 48
@@ -45,39 +48,6 @@ ErodeK make_ellipse(int margin) {
     for (int j = j1; j < j2; ++j) e.rows[i] |= 1u << j;
   }
   return e;
-}
-
-// src = M p  (p = (x, y, 1)) with kornia's homogeneous divide: scale = |z| > 1e-8 ? 1/(z + 1e-8) : 1
-__device__ __forceinline__ void apply_h(const float* __restrict__ m, float x, float y, float& sx, float& sy) {
-  const float nx = fmaf(m[0], x, fmaf(m[1], y, m[2]));
-  const float ny = fmaf(m[3], x, fmaf(m[4], y, m[5]));
-  const float z = fmaf(m[6], x, fmaf(m[7], y, m[8]));
-  const float sc = fabsf(z) > 1e-8f ? 1.0f / (z + 1e-8f) : 1.0f;
-  sx = nx * sc;
-  sy = ny * sc;
-}
-
-// grid_sample(mode='nearest', padding 'zeros') of an all-ones image: 1 iff the rounded coordinate is inside.
-__device__ __forceinline__ int inside_nearest(float sx, float sy, int H, int W) {
-  const float rx = rintf(sx), ry = rintf(sy);
-  return (rx >= 0.f && rx <= (float)(W - 1) && ry >= 0.f && ry <= (float)(H - 1)) ? 1 : 0;
-}
-
-// grid_sample(mode='bilinear', padding 'zeros', align_corners=True) of one channel.
-__device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, float sx, float sy, int H, int W) {
-  if (!(sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H)) return 0.f;  // also rejects NaN/inf
-  const float fx = floorf(sx), fy = floorf(sy);
-  const int x0 = (int)fx, y0 = (int)fy;
-  const float wx1 = sx - fx, wy1 = sy - fy;
-  const float wx0 = (fx + 1.f) - sx, wy0 = (fy + 1.f) - sy;
-  const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
-  const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
-  float v = 0.f;
-  if (yin0 && xin0) v = fmaf(__ldg(&img[(size_t)y0 * W + x0]), wx0 * wy0, v);
-  if (yin0 && xin1) v = fmaf(__ldg(&img[(size_t)y0 * W + x0 + 1]), wx1 * wy0, v);
-  if (yin1 && xin0) v = fmaf(__ldg(&img[(size_t)(y0 + 1) * W + x0]), wx0 * wy1, v);
-  if (yin1 && xin1) v = fmaf(__ldg(&img[(size_t)(y0 + 1) * W + x0 + 1]), wx1 * wy1, v);
-  return v;
 }
 
 // ---- tile classification -----------------------------------------------------------------------------------
@@ -170,7 +140,7 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hi
   const bool in_img = x < W && y < H;
   if (j == 0) {  // identity forward (export.py:93): the image itself, no mask
     if (in_img) {
-      warped[o] = __ldg(&src[(size_t)y * W + x]);
+      if (warped) warped[o] = __ldg(&src[(size_t)y * W + x]);
       mask[o] = 1;
     }
     return;
@@ -179,7 +149,10 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hi
   __syncthreads();
   const int cls = classify_tile(m, ek, tx0, ty0, H, W);  // identical in every warp of the block
   if (cls == kTileOutside) {
-    if (in_img) { warped[o] = 0.f; mask[o] = 0; }
+    if (in_img) {
+      if (warped) warped[o] = 0.f;
+      mask[o] = 0;
+    }
     return;
   }
   int mk = 1;
@@ -189,9 +162,11 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hi
     mk = eroded_bits(bits, ek, tx, ty);
   }
   if (in_img) {
-    float sx, sy;
-    apply_h(m, (float)x, (float)y, sx, sy);
-    warped[o] = bilinear_zero(src, sx, sy, H, W);
+    if (warped) {  // null: mask only (the fused encoder warps on the fly)
+      float sx, sy;
+      apply_h(m, (float)x, (float)y, sx, sy);
+      warped[o] = bilinear_zero(src, sx, sy, H, W);
+    }
     mask[o] = (uint8_t)mk;
   }
 }
@@ -402,7 +377,7 @@ __global__ void invert3x3_kernel(const float* __restrict__ in, int count, float*
 
 extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H,
                               int W, int margin, float* d_warped, uint8_t* d_mask, spn_stream stream) {
-  SPN_REQUIRE(ctx && d_images && d_warped && d_mask, "spn_warp_batch: null pointer");
+  SPN_REQUIRE(ctx && d_images && d_mask, "spn_warp_batch: null pointer");
   SPN_REQUIRE(n_images > 0 && n_h >= 0 && H > 0 && W > 0, "spn_warp_batch: bad shape");
   SPN_REQUIRE(n_h == 0 || d_hinv, "spn_warp_batch: d_hinv is null");
   // the reference's valid_border_margin == 0 path is shape-broken: unsupported

@@ -201,6 +201,27 @@ extern "C" int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, i
   return SPN_OK;
 }
 
+extern "C" int spn_encoder_forward_ha(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h,
+                                      int slot_begin, int n_slots, int H, int W, int mode, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_images, "spn_encoder_forward_ha: null pointer");
+  SPN_REQUIRE(n_h >= 0 && (n_h == 0 || d_hinv), "spn_encoder_forward_ha: d_hinv is null");
+  SPN_REQUIRE(n_images > 0 && slot_begin >= 0 && n_slots > 0 && (long long)slot_begin + n_slots <= (long long)n_images * (n_h + 1),
+              "spn_encoder_forward_ha: slot range [%d,%d) outside %d images x %d slots", slot_begin, slot_begin + n_slots, n_images, n_h + 1);
+  int rc = check_image_shape(n_slots, H, W);
+  if (rc) return rc;
+  SPN_REQUIRE(mode == SPN_MODE_F16 || mode == SPN_MODE_BF16,
+              "spn_encoder_forward_ha: the fused warp+encoder exists for the tensor-core modes only (fp32: spn_warp_batch + spn_encoder_forward)");
+  cudaStream_t s = (cudaStream_t)stream;
+  SPN_CUDA(cudaSetDevice(ctx->device));
+  for (int l = SPN_L_BLOCK1; l <= SPN_L_BLOCK8; ++l)
+    if (!ctx->layers[l].w32) { spn_set_error("spn_encoder_forward_ha: layer %d has no weights", l); return SPN_E_STATE; }
+  // n_h == 0 still goes through the slot path (slot == image)
+  rc = spn_tc_encoder_slots(ctx, d_images, n_h ? d_hinv : nullptr, n_h, slot_begin, n_slots, H, W, mode, s);
+  if (rc) return rc;
+  ctx->feat_B = n_slots; ctx->feat_H = H; ctx->feat_W = W; ctx->feat_mode = mode;
+  return SPN_OK;
+}
+
 static int check_feat(spn_ctx* ctx, int B, int H, int W, int mode, const char* who) {
   if (ctx->feat_mode != mode || ctx->feat_B != B || ctx->feat_H != H || ctx->feat_W != W) {
     spn_set_error("%s: no feature map for B=%d H=%d W=%d mode=%d (call spn_encoder_forward first)", who, B, H, W, mode);

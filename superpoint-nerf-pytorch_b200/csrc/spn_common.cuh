@@ -103,6 +103,11 @@ int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int
 int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_logits, cudaStream_t s);
 int spn_tc_descriptor_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw, cudaStream_t s);
 void spn_tc_destroy(spn_ctx* ctx);
+const float* spn_tc_bias(spn_ctx* ctx, int layer);
+int spn_tc_encoder_slots(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots,
+                         int H, int W, int mode, cudaStream_t s);
+int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots, int H,
+                        int W, int mode, const void* w1img, void* d_out, cudaStream_t s);
 float* spn_tc_logits_scratch(spn_ctx* ctx, int B, int H, int W);
 int spn_tc_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_in, int B, int H, int W, bool relu, bool pool,
                       float* d_out, cudaStream_t s);

@@ -1,0 +1,41 @@
+// Homography / sampling helpers shared by geometry.cu and front_tc.cu (kornia 0.7.0 warp_perspective semantics,
+// see oracle/kornia_shim.py for the restated algorithm).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace spngeom {
+
+// src = M p  (p = (x, y, 1)) with kornia's homogeneous divide: scale = |z| > 1e-8 ? 1/(z + 1e-8) : 1
+__device__ __forceinline__ void apply_h(const float* __restrict__ m, float x, float y, float& sx, float& sy) {
+  const float nx = fmaf(m[0], x, fmaf(m[1], y, m[2]));
+  const float ny = fmaf(m[3], x, fmaf(m[4], y, m[5]));
+  const float z = fmaf(m[6], x, fmaf(m[7], y, m[8]));
+  const float sc = fabsf(z) > 1e-8f ? 1.0f / (z + 1e-8f) : 1.0f;
+  sx = nx * sc;
+  sy = ny * sc;
+}
+
+// grid_sample(mode='nearest', padding 'zeros') of an all-ones image: 1 iff the rounded coordinate is inside.
+__device__ __forceinline__ int inside_nearest(float sx, float sy, int H, int W) {
+  const float rx = rintf(sx), ry = rintf(sy);
+  return (rx >= 0.f && rx <= (float)(W - 1) && ry >= 0.f && ry <= (float)(H - 1)) ? 1 : 0;
+}
+
+// grid_sample(mode='bilinear', padding 'zeros', align_corners=True) of one channel.
+__device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, float sx, float sy, int H, int W) {
+  if (!(sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H)) return 0.f;  // also rejects NaN/inf
+  const float fx = floorf(sx), fy = floorf(sy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float wx1 = sx - fx, wy1 = sy - fy;
+  const float wx0 = (fx + 1.f) - sx, wy0 = (fy + 1.f) - sy;
+  const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
+  const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
+  float v = 0.f;
+  if (yin0 && xin0) v = fmaf(__ldg(&img[(size_t)y0 * W + x0]), wx0 * wy0, v);
+  if (yin0 && xin1) v = fmaf(__ldg(&img[(size_t)y0 * W + x0 + 1]), wx1 * wy0, v);
+  if (yin1 && xin0) v = fmaf(__ldg(&img[(size_t)(y0 + 1) * W + x0]), wx0 * wy1, v);
+  if (yin1 && xin1) v = fmaf(__ldg(&img[(size_t)(y0 + 1) * W + x0 + 1]), wx1 * wy1, v);
+  return v;
+}
+
+}  // namespace spngeom

@@ -97,12 +97,16 @@ class HomographyAdaptation:
             homographies = self._homographies(NI, n_h, H, W, first_index)
         h = homographies.to(self.device, torch.float32).contiguous().view(NI, n_h, 3, 3)
         hinv = ctx.invert3x3(h)                                                  # export.py:49
-        warped, mask = ctx.warp_batch(imgs, hinv, self.ha["valid_border_margin"])  # export.py:51-66
+        fused = self.model.mode != 0 and self.ha.get("fused_warp", True)         # tensor-core modes: warp inside conv kernel
+        warped, mask = ctx.warp_batch(imgs, hinv, self.ha["valid_border_margin"], want_warped=not fused)  # export.py:51-66
         B = NI * (n_h + 1)
         probs = torch.empty((B, H, W), dtype=torch.float32, device=imgs.device)
         for s in range(0, B, self.max_forwards):                                 # export.py:69-70
             e = min(B, s + self.max_forwards)
-            self.model.prob_heatmap(warped[s:e], mask=mask[s:e], out=probs[s:e], slot=slot)
+            if fused:
+                self.model.prob_heatmap_ha(imgs, hinv, s, e - s, mask=mask[s:e], out=probs[s:e], slot=slot)
+            else:
+                self.model.prob_heatmap(warped[s:e], mask=mask[s:e], out=probs[s:e], slot=slot)
         agg = ctx.ha_aggregate(probs.view(NI, n_h + 1, H, W), h, self.ha["valid_border_margin"],
                                self.ha["aggregation"])                           # export.py:72-77,106-114
         return agg, h

@@ -140,3 +140,14 @@ class SuperPoint(nn.Module):
             ctx.encoder_forward(images, self.mode)
             prob, _ = ctx.detector_head_forward(B, H, W, self.mode, mask=mask, want_logits=False, out=out)
         return prob
+
+    @torch.no_grad()
+    def prob_heatmap_ha(self, images, hinv, slot_begin, n_slots, mask=None, out=None, slot=0):
+        """Heatmaps of the homography-adaptation slots [slot_begin, slot_begin + n_slots) of (images (NI,H,W),
+        hinv (NI,n_h,3,3)) with the warp fused into the first convolution kernel (tensor-core modes only)."""
+        ctx = self.native(slot)
+        _, H, W = images.shape
+        with torch.cuda.device(images.device):
+            ctx.encoder_forward_ha(images, hinv, slot_begin, n_slots, self.mode)
+            prob, _ = ctx.detector_head_forward(n_slots, H, W, self.mode, mask=mask, want_logits=False, out=out)
+        return prob

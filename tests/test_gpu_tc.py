@@ -90,3 +90,32 @@ def test_ha_fast_mode_keypoints_vs_golden(golden):
     print(f"fast-mode HA: heatmap rel err {err:.2e}, keypoints within 1px {a:.4f}/{b:.4f}")
     assert err < 2e-2
     assert a >= 0.97 and b >= 0.97
+
+
+def test_fused_front_end_matches_unfused(monkeypatch):
+    """warp + block_1 + block_2 fused in one tcgen05 kernel (front_tc.cu) vs the unfused kernels (warp_batch ->
+    conv1_c8 -> conv_tc): same heatmaps within fp16 rounding, for plain forwards and for warped HA slots, including
+    image sizes that are not multiples of the 8x16 tile."""
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    sd = O.make_state_dict("magicpoint", seed=7, logit_gain=8.0)
+    c = copy.deepcopy(MP_MODEL)
+    c["precision"] = "f16"
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    ctx = m.native()
+    for (NI, H, W, n_h) in [(2, 240, 320, 3), (1, 120, 160, 5), (3, 40, 72, 2)]:
+        imgs = torch.from_numpy(np.stack([smooth_image(H, W, 60 + i) for i in range(NI)])).cuda()
+        h, hinv = ctx.sample_homographies(HA_CFG["params"], seed=3, first_index=0, count=NI * n_h, H=H, W=W)
+        hinv = hinv.view(NI, n_h, 3, 3)
+        warped, mask = ctx.warp_batch(imgs, hinv, 3)
+        B = NI * (n_h + 1)
+        monkeypatch.setenv("SPN_TC_NOFUSE", "1")
+        ref = m.prob_heatmap(warped, mask=mask).clone()
+        monkeypatch.setenv("SPN_TC_NOFUSE", "0")
+        fused_plain = m.prob_heatmap(warped, mask=mask).clone()           # fused block_1+block_2, no warp
+        fused_ha = m.prob_heatmap_ha(imgs, hinv, 0, B, mask=mask).clone()  # fused warp+block_1+block_2
+        part = m.prob_heatmap_ha(imgs, hinv, 2, B - 3, mask=mask[2:B - 1]).clone()  # a slot sub-range
+        e1, e2 = rel_err(fused_plain.cpu().numpy(), ref.cpu().numpy()), rel_err(fused_ha.cpu().numpy(), ref.cpu().numpy())
+        print(f"{NI}x{H}x{W}: fused-vs-unfused rel err plain {e1:.2e}  ha {e2:.2e}")
+        assert e1 < 8e-3 and e2 < 8e-3  # two different fp16 roundings of block_1; each is gated against fp32 elsewhere
+        assert torch.equal(part, fused_ha[2:B - 1])
