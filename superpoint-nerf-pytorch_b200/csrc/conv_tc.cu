@@ -35,6 +35,8 @@ constexpr int kTW = 8, kTH = 16;              // output tile: 8 x 16 pixels = 12
 constexpr int kThreads = 192;
 constexpr int kWBlockBytes = 8192;            // weights of one (cin block, tap): 4 k-steps x 2 chunks x 64 cout x 16 B
 constexpr int kMaxStages = 6;
+constexpr int kBiasBlockBytes = 2048;         // bias as operand B: [chunk 2][cout 64][8], k 0 / 1 = hi / lo halves
+constexpr int kOnesBytes = 4096;              // constant operand A of the bias MMA: [chunk 2][128 rows][8]
 
 struct TcParams {
   int n_img, H, W;        // input == conv-output spatial size
@@ -55,6 +57,14 @@ struct TcParams {
   const void* wimg;       // [cout_slices][cin_blocks][taps][4][2][64][8] halfs
 };
 
+// Constant A operand of the bias MMA: row r = (1, 1, 0, ..., 0) in K chunk 0, zeros in chunk 1.
+__device__ __forceinline__ void fill_ones_operand(uint8_t* ones, int is_bf16, int tid, int nthreads) {
+  const uint32_t one2 = is_bf16 ? 0x3F803F80u : 0x3C003C00u;
+  for (int i = tid; i < kOnesBytes / 16; i += nthreads)
+    reinterpret_cast<uint4*>(ones)[i] = i < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ main kernel
 template <int TAPS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -62,15 +72,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_w, bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias_s[64];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int halo = TAPS == 9 ? 1 : 0;
   constexpr int PW = kTW + 2 * halo, PH = kTH + 2 * halo;
   constexpr uint32_t ch_stride = (uint32_t)PH * PW * 16;  // bytes between 8-channel groups inside a slab
-  const int wbytes = p.cin_blocks * TAPS * kWBlockBytes;
-  uint8_t* wsm = smem;                                    // this CTA's weight slice, resident for the whole kernel
-  uint8_t* slab0 = smem + ((wbytes + 1023) & ~1023);
+  const int wbytes = p.cin_blocks * TAPS * kWBlockBytes + kBiasBlockBytes;
+  uint8_t* wsm = smem;                                    // this CTA's weight slice (+ bias block), resident
+  uint8_t* ones = smem + ((wbytes + 1023) & ~1023);       // constant A operand of the bias MMA
+  uint8_t* slab0 = ones + kOnesBytes;
 
   const int slice = blockIdx.x % p.cout_slices;
   const int cta_in_slice = blockIdx.x / p.cout_slices, ctas_per_slice = gridDim.x / p.cout_slices;
@@ -83,7 +93,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 64) bias_s[threadIdx.x] = p.bias[slice * 64 + threadIdx.x];
+  fill_ones_operand(ones, p.is_bf16, threadIdx.x, kThreads);
   if (warp == 1) {  // TMEM: 2 accumulators x 64 fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -98,7 +108,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     if (elect_one()) {
       mbar_expect_tx(&bar_w, (uint32_t)wbytes);
       const uint8_t* wsrc = (const uint8_t*)p.wimg + (size_t)slice * wbytes;
-      for (int o = 0; o < wbytes; o += kWBlockBytes) bulk_load(wsm + o, wsrc + o, kWBlockBytes, &bar_w);
+      for (int o = 0; o + kWBlockBytes <= wbytes; o += kWBlockBytes) bulk_load(wsm + o, wsrc + o, kWBlockBytes, &bar_w);
+      bulk_load(wsm + wbytes - kBiasBlockBytes, wsrc + wbytes - kBiasBlockBytes, kBiasBlockBytes, &bar_w);
     }
     int stage = 0;
     uint32_t phase = 0;
@@ -150,7 +161,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
             }
           }
           umma_commit(&bar_empty[stage]);  // frees the slab once these MMAs have read it
-          if (cb == p.cin_blocks - 1) umma_commit(&bar_tfull[acc]);  // accumulator complete -> epilogue
+          if (cb == p.cin_blocks - 1) {
+            // + bias: D += ones[128 x 16] . biasB[64 x 16]  (k 0/1 = hi/lo halves of the folded bias)
+            const uint32_t o_lo = (smem_u32(ones) >> 4) | ((2048u >> 4) << 16);
+            const uint32_t bb_lo = ((w_addr + (uint32_t)p.cin_blocks * (TAPS * kWBlockBytes)) >> 4) | b_lo_c;
+            umma_f16_2w(d_tmem, o_lo, (128u >> 4) | (1u << 14), bb_lo, b_hi, idesc, 1u);
+            umma_commit(&bar_tfull[acc]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -183,9 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
         uint32_t h2[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          float a = __uint_as_float(v[2 * c]) + bias_s[2 * c], b = __uint_as_float(v[2 * c + 1]) + bias_s[2 * c + 1];
-          if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          h2[c] = pack2(a, b, p.is_bf16);
+          h2[c] = pack2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]), p.is_bf16);  // bias is already in D
         }
         int oy = y, ox = x, Ho = p.H, Wo = p.W;
         bool writer = (y < p.H) && (x < p.W);
@@ -197,6 +212,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           }
           writer = writer && ((g & 1) == 0) && ((r & 1) == 0);
           oy = y >> 1; ox = x >> 1; Ho = p.H >> 1; Wo = p.W >> 1;
+        }
+        if (p.relu) {  // after the pool: max commutes with ReLU
+#pragma unroll
+          for (int c = 0; c < 32; ++c) h2[c] = max2(h2[c], 0u, p.is_bf16);
         }
         if (writer) {
           const int cgroups = p.cout_slices * 8;
@@ -214,7 +233,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
           for (int c = 0; c < 64; ++c) {
             const int co = slice * 64 + c;
             if (co < p.cout) {
-              float a = __uint_as_float(v[c]) + bias_s[c];
+              float a = __uint_as_float(v[c]);
               if (p.relu) a = fmaxf(a, 0.f);
               o[(((size_t)n * p.cout + co) * p.H + y) * p.W + x] = a;
             }
@@ -398,8 +417,8 @@ int launch_conv_tc(spn_ctx* ctx, int layer, int mode, const void* in, void* out,
   const int PW = kTW + 2 * halo, PH = kTH + 2 * halo;
   p.slab_bytes = 8 * PH * PW * 16;
   p.stage_bytes = (p.slab_bytes + 1023) & ~1023;
-  const int wbytes = p.cin_blocks * p.taps * kWBlockBytes;
-  const int wres = (wbytes + 1023) & ~1023;
+  const int wbytes = p.cin_blocks * p.taps * kWBlockBytes + kBiasBlockBytes;
+  const int wres = ((wbytes + 1023) & ~1023) + kOnesBytes;
   const int max_dyn = 227 * 1024 - 2048;  // leave room for the static barriers / bias
   p.stages = (max_dyn - wres - 1024) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -491,11 +510,17 @@ int spn_tc_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float
   SPN_CUDA(cudaMalloc((void**)&st->bias_pad[layer], bias.size() * sizeof(float)));
   SPN_CUDA(cudaMemcpy(st->bias_pad[layer], bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
   // operand-B image: [slice][cin block][tap][k-step 4][chunk 2][cout 64][8 cin]  (SWIZZLE_NONE K-major core matrices)
-  const size_t n16 = (size_t)slices * cbs * taps * 4 * 2 * 64 * 8;
+  // followed, per slice, by the bias block [chunk 2][cout 64][8]: k 0 = hi, k 1 = lo 16-bit halves of the folded bias
+  const size_t n16 = (size_t)slices * ((size_t)cbs * taps * 4 * 2 * 64 * 8 + 2 * 64 * 8);
   for (int bf = 0; bf < 2; ++bf) {
     std::vector<uint16_t> img(n16, 0);
     size_t o = 0;
-    for (int sl = 0; sl < slices; ++sl)
+    auto from16 = [&](uint16_t h) {
+      if (bf) { __nv_bfloat16 v = *reinterpret_cast<__nv_bfloat16*>(&h); return __bfloat162float(v); }
+      __half v = *reinterpret_cast<__half*>(&h);
+      return __half2float(v);
+    };
+    for (int sl = 0; sl < slices; ++sl) {
       for (int cb = 0; cb < cbs; ++cb)
         for (int t = 0; t < taps; ++t)
           for (int kk = 0; kk < 4; ++kk)
@@ -505,6 +530,16 @@ int spn_tc_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float
                   const int c = sl * 64 + co, ci = cb * 64 + kk * 16 + j * 8 + e;
                   if (c < L.cout) img[o] = to16(h_wfold[((size_t)c * L.cin + ci) * taps + t], bf);
                 }
+      for (int co = 0; co < 64; ++co) {
+        const int c = sl * 64 + co;
+        if (c < L.cout) {
+          const uint16_t hi = to16(h_bfold[c], bf);
+          img[o + (size_t)co * 8] = hi;
+          img[o + (size_t)co * 8 + 1] = to16(h_bfold[c] - from16(hi), bf);
+        }
+      }
+      o += 2 * 64 * 8;
+    }
     if (L.w16[bf]) { cudaFree(L.w16[bf]); L.w16[bf] = nullptr; }
     SPN_CUDA(cudaMalloc(&L.w16[bf], n16 * 2));
     SPN_CUDA(cudaMemcpy(L.w16[bf], img.data(), n16 * 2, cudaMemcpyHostToDevice));

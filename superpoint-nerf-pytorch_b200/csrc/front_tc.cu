@@ -7,14 +7,15 @@
 // VGG_Block 1 and 2 (models/model_utils/VGG_Backbone.py:23-36, 60-63).
 //
 // Per CTA tile (8 x 16 output pixels of block_2 before pooling = M 128), pipelined over tiles by warp role:
-//   P  warps 10-13  bilinear-sample the 12 x 20 warped-image patch, build block_1's im2col operand A1
+//   P  warps 10-17  bilinear-sample the 12 x 20 warped-image patch, build block_1's im2col operand A1
 //                   (256 rows = the 10 x 18 halo pixels (180 used), K = 9 taps padded to 16, fp16) in SMEM
 //   M  warp 1       MMA1: D1 = A1 . W1 (2 x M128 N64 K16) into TMEM, issued one tile AHEAD of
 //                   MMA2: D2 += slab(tap) . W2(tap) (36 x M128 N64 K16, weights resident in SMEM)
 //   E1 warps 6-9    D1 (bias already added through A1's ones columns, rows outside the image exactly 0 = block_2's
 //                   zero padding) -> ReLU -> fp16 -> the slab
 //                   [chunk][halo row][halo col][8] that MMA2's nine shifted descriptors read
-//   E2 warps 2-5    D2 -> +bias2 -> ReLU -> 2x2 max-pool (two shfl.xor) -> 16-byte C8 stores
+//   E2 warps 2-5    D2 (bias2 added by one extra MMA against a constant ones operand) -> 2x2 max-pool (two shfl.xor)
+//                   -> ReLU -> 16-byte C8 stores
 //   warp 0          weight loader (cp.async.bulk)
 // All hand-offs are mbarriers (generic-proxy SMEM writes are published to the tensor core with fence.proxy.async).
 #include "spn_common.cuh"
@@ -33,12 +34,15 @@ constexpr int kQW = kTW + 4, kQH = kTH + 4;          // warped-image patch: 12 x
 constexpr uint32_t kChStride = (uint32_t)kHalo * 16;  // slab bytes between 8-channel groups (2880)
 constexpr int kSlabBytes = 8 * kHalo * 16;            // 23040
 constexpr int kStageBytes = (kSlabBytes + 1023) & ~1023;
-constexpr int kW2Bytes = 9 * 8192;                    // block_2 weights, one 64-channel slice
+constexpr int kW2Bytes = 9 * 8192 + 2048;             // block_2 weights, one 64-channel slice, + its bias block
+constexpr int kOnesBytes = 4096;                      // constant operand A of the bias MMA
 constexpr int kW1Bytes = 2 * 64 * 16;                 // block_1 weights as operand B: [chunk 2][cout 64][8]
 constexpr int kA1Rows = 256;
 constexpr int kA1Bytes = 2 * kA1Rows * 16;            // [chunk 2][row 256][8 halfs]
 constexpr int kStages = 4;
-constexpr int kThreads = 448;                         // 14 warps
+constexpr int kNA1 = 3;                               // A1 / D1 buffers: MMA1 runs two tiles ahead of MMA2
+constexpr int kThreads = 576;                         // 18 warps
+constexpr int kPThreads = 256;                        // P role: warps 10-17
 
 struct FrontParams {
   const float* images;   // [n_src][H][W] fp32
@@ -65,17 +69,16 @@ __device__ __forceinline__ uint16_t to16(float v, int bf) {
 
 __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a1_full[2], bar_a1_empty[2], bar_d1_full[2], bar_d1_empty[2],
+  __shared__ __align__(8) uint64_t bar_w, bar_a1_full[kNA1], bar_a1_empty[kNA1], bar_d1_full[kNA1], bar_d1_empty[kNA1],
       bar_slab_full[kStages], bar_slab_empty[kStages], bar_d2_full[2], bar_d2_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias2_s[64];
-  __shared__ __align__(16) uint16_t patch_s[2][kQH * kQW];
-  __shared__ float hm_s[2][12];
+  __shared__ __align__(16) uint16_t patch_s[kNA1][kQH * kQW];
 
-  uint8_t* w2s = smem;                                  // 73728
+  uint8_t* w2s = smem;                                  // 75776
   uint8_t* w1s = smem + kW2Bytes;                       // 2048
-  uint8_t* a1s = w1s + kW1Bytes;                        // 2 x 8192
-  uint8_t* slab0 = a1s + 2 * kA1Bytes;                  // kStages x 23552  (1024-aligned: 73728+2048+16384 = 92160)
+  uint8_t* a1s = w1s + kW1Bytes;                        // kNA1 x 8192   (at 77824)
+  uint8_t* ones = a1s + kNA1 * kA1Bytes;                // 4096          (at 102400)
+  uint8_t* slab0 = ones + kOnesBytes;                   // kStages x 23552  (at 106496 = 104 x 1024)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -83,22 +86,26 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
 
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_a1_full[i], 128); mbar_init(&bar_a1_empty[i], 1);
+    for (int i = 0; i < kNA1; ++i) {
+      mbar_init(&bar_a1_full[i], kPThreads); mbar_init(&bar_a1_empty[i], 1);
       mbar_init(&bar_d1_full[i], 1);   mbar_init(&bar_d1_empty[i], 128);
-      mbar_init(&bar_d2_full[i], 1);   mbar_init(&bar_d2_empty[i], 128);
     }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_d2_full[i], 1); mbar_init(&bar_d2_empty[i], 128); }
     for (int i = 0; i < kStages; ++i) { mbar_init(&bar_slab_full[i], 128); mbar_init(&bar_slab_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 64) bias2_s[threadIdx.x] = p.bias2[threadIdx.x];
   // A1 rows >= 180 are never written again: zero both buffers once
-  for (int i = threadIdx.x; i < 2 * kA1Bytes / 16; i += kThreads) reinterpret_cast<uint4*>(a1s)[i] = make_uint4(0, 0, 0, 0);
-  if (warp == 1) {  // TMEM: D2 2 x 64 columns, D1 2 buffers x 2 halves x 64 columns -> 384, allocate 512
+  for (int i = threadIdx.x; i < kNA1 * kA1Bytes / 16; i += kThreads) reinterpret_cast<uint4*>(a1s)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 1) {  // TMEM: D2 2 x 64 columns + D1 3 buffers x 2 halves x 64 columns = 512 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the zero fill above is read by the tensor core
+  {
+    const uint32_t one2 = p.is_bf16 ? 0x3F803F80u : 0x3C003C00u;
+    for (int i = threadIdx.x; i < kOnesBytes / 16; i += kThreads)
+      reinterpret_cast<uint4*>(ones)[i] = i < 128 ? make_uint4(one2, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the fills above are read by the tensor core
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -110,7 +117,8 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
     // ===================== weight loader =====================
     if (elect_one()) {
       mbar_expect_tx(&bar_w, (uint32_t)(kW2Bytes + kW1Bytes));
-      for (int o = 0; o < kW2Bytes; o += 8192) bulk_load(w2s + o, (const uint8_t*)p.w2img + o, 8192, &bar_w);
+      for (int o = 0; o + 8192 <= kW2Bytes; o += 8192) bulk_load(w2s + o, (const uint8_t*)p.w2img + o, 8192, &bar_w);
+      bulk_load(w2s + 9 * 8192, (const uint8_t*)p.w2img + 9 * 8192, 2048, &bar_w);
       bulk_load(w1s, p.w1img, kW1Bytes, &bar_w);
     }
   } else if (warp == 1) {
@@ -127,8 +135,8 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
     const uint32_t d1_col = tmem_base + 128;
 
     auto issue_mma1 = [&](int i) {  // block_1 for local tile i: D1[b][h] = A1[b] rows h*128.. times W1
-      const int b = i & 1;
-      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const int b = i % kNA1;
+      const uint32_t ph = (uint32_t)(i / kNA1) & 1u;
       mbar_wait(&bar_a1_full[b], ph);
       mbar_wait(&bar_d1_empty[b], ph ^ 1u);
       tc_fence_after();
@@ -144,10 +152,12 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       __syncwarp();
     };
 
+    // Tensor-pipe order: MMA1(0) MMA1(1) | MMA2(0) MMA1(2) | MMA2(1) MMA1(3) | ...  D1(i+1) is complete before MMA2(i)
+    // starts, so E1 turns it into slab(i+1) while MMA2(i) runs, and P has two tile times to deliver A1(i+2).
     int i = 0;
     if ((int)blockIdx.x < n_tiles) issue_mma1(0);
+    if ((int)(blockIdx.x + gridDim.x) < n_tiles) issue_mma1(1);
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      if (t + (int)gridDim.x < n_tiles) issue_mma1(i + 1);  // one tile ahead, so E1 overlaps MMA2 of this tile
       const int stage = i % kStages, acc = i & 1;
       const uint32_t sph = (uint32_t)(i / kStages) & 1u, aph = (uint32_t)(i >> 1) & 1u;
       mbar_wait(&bar_slab_full[stage], sph);
@@ -167,28 +177,36 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
           }
         }
         umma_commit(&bar_slab_empty[stage]);
+        // + bias2: D2 += ones[128 x 16] . biasB[64 x 16]
+        umma_f16_2w(d2, (smem_u32(ones) >> 4) | ((2048u >> 4) << 16), (128u >> 4) | (1u << 14), w2_lo + ((9u * 8192u) >> 4), hi_b,
+                    idesc, 1u);
         umma_commit(&bar_d2_full[acc]);
       }
       __syncwarp();
+      if (t + 2 * (int)gridDim.x < n_tiles) issue_mma1(i + 2);
     }
   } else if (warp >= 10) {
     // ===================== P: warped patch + im2col operand of block_1 =====================
-    const int pt = threadIdx.x - 320;  // 0..127
+    const int pt = threadIdx.x - 320;  // 0..255
     int i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      const int b = i & 1;
-      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      const int b = i % kNA1;
+      const uint32_t ph = (uint32_t)(i / kNA1) & 1u;
       const int ls = t / tiles_per_img, rr = t - ls * tiles_per_img;
       const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
       const int slot = p.slot_begin + ls;
       const int src = p.hinv ? slot / (p.n_h + 1) : slot;
       const int j = p.hinv ? slot - src * (p.n_h + 1) : 0;
       const float* img = p.images + (size_t)src * p.H * p.W;
-      mbar_wait(&bar_a1_empty[b], ph ^ 1u);  // MMA1 of tile i-2 has consumed A1[b] (and patch_s[b] long before)
-      if (j > 0 && pt < 9) hm_s[b][pt] = __ldg(&p.hinv[((size_t)src * p.n_h + (j - 1)) * 9 + pt]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&bar_a1_empty[b], ph ^ 1u);  // MMA1 of tile i-3 has consumed A1[b] (and patch_s[b] long before)
+      float hm[9];
+      if (j > 0) {  // same 36 bytes for every thread of the tile: L1 broadcast
+        const float* hp = p.hinv + ((size_t)src * p.n_h + (j - 1)) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) hm[k] = __ldg(hp + k);
+      }
       // 1. the 12 x 20 patch of the warped image around the tile (zero outside the frame = block_1's padding)
-      for (int s = pt; s < kQH * kQW; s += 128) {
+      for (int s = pt; s < kQH * kQW; s += kPThreads) {
         const int py = s / kQW, px = s - py * kQW;
         const int y = ty * kTH - 2 + py, x = tx * kTW - 2 + px;
         float v = 0.f;
@@ -197,18 +215,18 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
             v = __ldg(&img[(size_t)y * p.W + x]);
           } else {
             float sx, sy;
-            apply_h(hm_s[b], (float)x, (float)y, sx, sy);
+            apply_h(hm, (float)x, (float)y, sx, sy);
             v = bilinear_zero(img, sx, sy, p.H, p.W);
           }
         }
         patch_s[b][s] = to16(v, p.is_bf16);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       // 2. A1 row r = halo pixel (hy, hx): its 3x3 neighbourhood (K 0..8), then two constant-one columns that
       //    multiply the (hi, lo) bias rows of W1.  Halo pixels outside the image get an all-zero row, so block_1's
       //    output there is exactly 0 = block_2's zero padding.
       const uint32_t one16 = p.is_bf16 ? 0x3F80u : 0x3C00u;
-      for (int r = pt; r < kHalo; r += 128) {
+      for (int r = pt; r < kHalo; r += kPThreads) {
         const int hy = r / kPW, hx = r - hy * kPW;
         const int gy = ty * kTH - 1 + hy, gx = tx * kTW - 1 + hx;
         uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
@@ -233,8 +251,8 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
     const int q = warp & 3;
     int i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
-      const int b = i & 1, stage = i % kStages;
-      const uint32_t ph = (uint32_t)(i >> 1) & 1u, sph = (uint32_t)(i / kStages) & 1u;
+      const int b = i % kNA1, stage = i % kStages;
+      const uint32_t ph = (uint32_t)(i / kNA1) & 1u, sph = (uint32_t)(i / kStages) & 1u;
       mbar_wait(&bar_d1_full[b], ph);
       mbar_wait(&bar_slab_empty[stage], sph ^ 1u);
       tc_fence_after();
@@ -289,15 +307,11 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       mbar_arrive(&bar_d2_empty[acc]);
       uint32_t h2[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float a = fmaxf(__uint_as_float(v[2 * c]) + bias2_s[2 * c], 0.f);
-        const float bb = fmaxf(__uint_as_float(v[2 * c + 1]) + bias2_s[2 * c + 1], 0.f);
-        h2[c] = pack2(a, bb, p.is_bf16);
-      }
+      for (int c = 0; c < 32; ++c) h2[c] = pack2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]), p.is_bf16);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
+      for (int c = 0; c < 32; ++c) {  // bias is already in D2; pool first, ReLU after (max commutes)
         h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 1), p.is_bf16);
-        h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 8), p.is_bf16);
+        h2[c] = max2(max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 8), p.is_bf16), 0u, p.is_bf16);
       }
       if (y < p.H && x < p.W && (g & 1) == 0 && (r & 1) == 0) {
         uint4* o = reinterpret_cast<uint4*>(p.out);
@@ -331,7 +345,7 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
   p.H = H; p.W = W; p.tiles_x = spn_cdiv(W, kTW); p.tiles_y = spn_cdiv(H, kTH); p.is_bf16 = bf;
   p.w1img = w1img; p.bias1 = ctx->layers[SPN_L_BLOCK1].bias; p.w2img = L2.w16[bf]; p.bias2 = spn_tc_bias(ctx, SPN_L_BLOCK2);
   p.out = d_out;
-  const size_t dyn = (size_t)kW2Bytes + kW1Bytes + 2 * kA1Bytes + (size_t)kStages * kStageBytes + 1024;
+  const size_t dyn = (size_t)kW2Bytes + kW1Bytes + kNA1 * kA1Bytes + kOnesBytes + (size_t)kStages * kStageBytes + 1024;
   SPN_CUDA(cudaFuncSetAttribute(front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   const long long tiles = (long long)n_slots * p.tiles_x * p.tiles_y;
   const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
