@@ -42,6 +42,8 @@ HA_CFG = {"num": NUM_H, "aggregation": "sum", "filter_counts": 0, "valid_border_
                      "perspective_amplitude_x": 0.2, "perspective_amplitude_y": 0.2, "allow_artifacts": True,
                      "patch_ratio": 0.85, "max_angle": 1.57}}
 # exact FLOPs (2*MACs) of one MagicPoint forward at 240x320, per layer
+# in the tensor-core modes block_1 is fused into block_2's kernel (front_tc.cu): its 0.088 GFLOP are then timed (and
+# counted) under "backbone.block_2"
 LAYER_FLOPS = {"backbone.block_1": 0.088e9, "backbone.block_2": 5.662e9, "backbone.block_3": 1.416e9,
                "backbone.block_4": 1.416e9, "backbone.block_5": 0.708e9, "backbone.block_6": 1.416e9,
                "backbone.block_7": 0.354e9, "backbone.block_8": 0.354e9, "detector_head.convPa": 0.708e9,
@@ -50,12 +52,13 @@ FLOPS_PER_IMAGE = 1.2161e12
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
-def ncu_block2_traffic_per_forward():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the block_2 launch in the committed `ncu --set full` capture
-    (profiles/r1_kernels.json, 100 forwards per launch) -> bytes per forward, or None."""
+def ncu_block2_traffic_per_forward(fused=True):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch in the committed `ncu --set full`
+    capture (profiles/r1_kernels_final.json, 100 forwards per launch) -> bytes per forward, or None."""
     try:
-        ks = json.loads((ROOT / "profiles" / "r1_kernels.json").read_text())
-        k = max((k for k in ks if "conv_tc_kernel<9>" in k["kernel"]), key=lambda k: k["time_us"])
+        ks = json.loads((ROOT / "profiles" / "r1_kernels_final.json").read_text())
+        pat = "front_tc_kernel" if fused else "conv_tc_kernel<9>"
+        k = max((k for k in ks if pat in k["kernel"]), key=lambda k: k["time_us"])
         return (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6 / 100.0
     except Exception:
         return None
@@ -286,6 +289,8 @@ def run_native(args):
         if not n:
             return None
         fl = LAYER_FLOPS[name] * forwards
+        if name == "backbone.block_2" and "backbone.block_1" not in prof:
+            fl += LAYER_FLOPS["backbone.block_1"] * forwards   # fused front end
         ach = fl / (t / 1e3) / 1e12
         return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / pk["bf16_tflops_sustained"], "ms_per_launch": t / n, "launches": n}
@@ -313,7 +318,8 @@ def run_native(args):
         fwd_per_launch = forwards / max(dom["launches"], 1)
         roof = {"bound": "tensor", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"],
                 "traffic": (tpf * fwd_per_launch) if tpf else None, "traffic_unit": "bytes per launch (ncu dram read+write)",
-                "algorithmic_flops_per_launch": LAYER_FLOPS["backbone.block_2"] * fwd_per_launch,
+                "algorithmic_flops_per_launch": (LAYER_FLOPS["backbone.block_2"] + (LAYER_FLOPS["backbone.block_1"]
+                                                 if "backbone.block_1" not in prof else 0.0)) * fwd_per_launch,
                 "ms_per_launch": dom["ms_per_launch"], "kernel": "backbone.block_2 3x3 conv 64->64 @240x320 (implicit GEMM M=pixels N=64 K=576)",
                 "peak_source": f"{pk_kind} bf16_tflops_sustained", "share_of_step": (prof["backbone.block_2"][0] / total_kernel_ms)
                 if total_kernel_ms else None}
