@@ -330,3 +330,57 @@ def test_hpatches_exports_layout(P, golden, tmp_path, monkeypatch):
     pts = g["des_pts"]
     assert rel_err(des["desc"][pts[:, 0], pts[:, 1]], g["des_desc_at_pts"]) < STRICT
     assert rel_err(des["warped_desc"][pts[:, 0], pts[:, 1]], g["des_warped_desc_at_pts"]) < STRICT
+
+
+def test_ha_max_aggregation_and_no_ha_vs_oracle(P, tmp_path, monkeypatch):
+    from superpoint_nerf_pytorch_b200 import settings
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import ExportDetections, HomographyAdaptation
+    sd = O.make_state_dict("magicpoint", seed=9, logit_gain=10.0)
+    m = make_model(MP_MODEL, sd)
+    ha = copy.deepcopy(HA_CFG)
+    ha.update(num=5, aggregation="max", valid_border_margin=2)
+    mcfg = copy.deepcopy(MP_MODEL)
+    mcfg["detector_head"]["top_k"] = 40
+    cfg = {"data": {"experiment_name": "mx"}, "homography_adaptation": ha, "model": mcfg}
+    img = torch.from_numpy(smooth_image(96, 128, 77))[None, None]
+    np.random.seed(4)
+    want = O.homography_adaptation(sd, img, cfg, nms_fn=O.box_nms_c)
+    eng = HomographyAdaptation(cfg, m, "cuda")
+    heat, _ = eng.heatmaps(img.cuda(), homographies=want["homographies"].view(1, 4, 3, 3))
+    ref = want["mean_prob"].numpy()
+    bad = np.abs(heat[0].cpu().numpy() - ref) > STRICT * np.abs(ref).max()
+    assert bad.mean() < 1e-3
+    kp = eng.keypoints(heat)[0]
+    assert len(kp) == 40 == len(want["keypoints"])                 # top_k honoured
+    a, b = keypoint_agreement(kp, want["keypoints"])
+    assert a >= 0.95 and b >= 0.95
+    # enable_HA=False: plain forward + NMS (export.py:93,116-125)
+    monkeypatch.setattr(settings, "EXPER_PATH", str(tmp_path))
+    ExportDetections(cfg, m, [{"raw": {"image": img}, "name": ["a"]}], "validation", False, "cuda")
+    got = np.load(Path(tmp_path, "outputs", "mx", "validation", "a.npy"))
+    feat = O.backbone_forward(sd, img)
+    p0 = O.detector_head_forward(sd, feat, 8, nms=0)["prob_heatmap"][0]
+    ref_kp = np.argwhere(O.box_nms_c(p0, 4, 0.1, 0.015, 40).numpy() >= 0.015)
+    a, b = keypoint_agreement(got, ref_kp)
+    assert a >= 0.95 and b >= 0.95 and len(got) == len(ref_kp)
+
+
+def test_export_batching_and_streams_are_transparent(P, tmp_path, monkeypatch):
+    """images_per_launch / streams only change scheduling: the files written are identical."""
+    from superpoint_nerf_pytorch_b200 import settings
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import ExportDetections
+    sd = O.make_state_dict("magicpoint", seed=5, logit_gain=10.0)
+    m = make_model(MP_MODEL, sd, precision="f16")
+    imgs = [torch.from_numpy(smooth_image(64, 96, 200 + i))[None, None] for i in range(5)]
+    loader = [{"raw": {"image": im}, "name": [f"im{i}"]} for i, im in enumerate(imgs)]
+    outs = []
+    for tag, extra in (("one", {"images_per_launch": 1, "streams": 1}), ("many", {"images_per_launch": 4, "streams": 2})):
+        ha = copy.deepcopy(HA_CFG)
+        ha.update(num=6, sampler="device", seed=11, **extra)
+        cfg = {"data": {"experiment_name": tag}, "homography_adaptation": ha, "model": copy.deepcopy(MP_MODEL)}
+        monkeypatch.setattr(settings, "EXPER_PATH", str(tmp_path))
+        ExportDetections(cfg, m, loader, "training", True, "cuda")
+        outs.append([np.load(Path(tmp_path, "outputs", tag, "training", f"im{i}.npy")) for i in range(5)])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert all(len(a) > 0 for a in outs[0])
