@@ -51,9 +51,7 @@ struct TcParams {
   int stages;
   int stage_bytes;        // slab bytes rounded up to 1024
   int slab_bytes;         // exact TMA transaction bytes
-  int dbg;                // bit0: swap LBO/SBO of A, bit1: swap LBO/SBO of B
   void* out;
-  const float* bias;      // [cout_slices * 64]
   const void* wimg;       // [cout_slices][cin_blocks][taps][4][2][64][8] halfs
 };
 
@@ -132,8 +130,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams p) {
     // instruction descriptor: D=f32, A=B=f16|bf16, both K-major, N=64, M=128
     const uint32_t fmt = p.is_bf16 ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t a_lbo = (p.dbg & 1) ? (uint32_t)PW * 16 : ch_stride, a_sbo = (p.dbg & 1) ? ch_stride : (uint32_t)PW * 16;
-    const uint32_t b_lbo = (p.dbg & 2) ? 128u : 1024u, b_sbo = (p.dbg & 2) ? 1024u : 128u;
+    // operand A (slab): LBO = stride between 8-channel groups, SBO = stride between 8-pixel rows of the halo tile;
+    // operand B (weights): LBO = 1024 B between the two K chunks, SBO = 128 B between groups of 8 output channels
+    const uint32_t a_lbo = ch_stride, a_sbo = (uint32_t)PW * 16;
+    const uint32_t b_lbo = 1024u, b_sbo = 128u;
     const uint32_t a_hi = (a_sbo >> 4) | (1u << 14), b_hi = (b_sbo >> 4) | (1u << 14);  // SBO | descriptor version 1
     const uint32_t a_lo_c = (a_lbo >> 4) << 16, b_lo_c = (b_lbo >> 4) << 16;
     mbar_wait(&bar_w, 0);
@@ -423,9 +423,7 @@ int launch_conv_tc(spn_ctx* ctx, int layer, int mode, const void* in, void* out,
   p.stages = (max_dyn - wres - 1024) / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   SPN_REQUIRE(p.stages >= 2, "layer %d does not fit in shared memory (weights %d bytes)", layer, wbytes);
-  const char* dbg = getenv("SPN_TC_DEBUG");
-  p.dbg = dbg ? atoi(dbg) : 0;
-  p.out = out; p.bias = st->bias_pad[layer]; p.wimg = L.w16[bf];
+  p.out = out; p.wimg = L.w16[bf];
   const size_t dyn = (size_t)wres + (size_t)p.stages * p.stage_bytes + 1024;
 
   CUtensorMap tmap;

@@ -51,10 +51,8 @@ struct FrontParams {
   int slot_begin, n_slots;
   int H, W, tiles_x, tiles_y;
   int is_bf16;
-  const void* w1img;     // operand-B image of block_1
-  const float* bias1;    // [64]
-  const void* w2img;     // operand-B image of block_2 (72 KB)
-  const float* bias2;    // [64]
+  const void* w1img;     // operand-B image of block_1 (taps + bias rows)
+  const void* w2img;     // operand-B image of block_2 (72 KB) followed by its 2 KB bias block
   void* out;             // C8 [n_slots][8][H/2][W/2][8]
 };
 
@@ -343,7 +341,7 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
   memset(&p, 0, sizeof(p));
   p.images = d_images; p.hinv = d_hinv; p.n_h = n_h; p.slot_begin = slot_begin; p.n_slots = n_slots;
   p.H = H; p.W = W; p.tiles_x = spn_cdiv(W, kTW); p.tiles_y = spn_cdiv(H, kTH); p.is_bf16 = bf;
-  p.w1img = w1img; p.bias1 = ctx->layers[SPN_L_BLOCK1].bias; p.w2img = L2.w16[bf]; p.bias2 = spn_tc_bias(ctx, SPN_L_BLOCK2);
+  p.w1img = w1img; p.w2img = L2.w16[bf];
   p.out = d_out;
   const size_t dyn = (size_t)kW2Bytes + kW1Bytes + kNA1 * kA1Bytes + kOnesBytes + (size_t)kStages * kStageBytes + 1024;
   SPN_CUDA(cudaFuncSetAttribute(front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

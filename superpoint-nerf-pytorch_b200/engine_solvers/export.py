@@ -112,20 +112,38 @@ class HomographyAdaptation:
         return agg, h
 
     @torch.no_grad()
-    def keypoints(self, heat):
-        """box_nms + threshold + nonzero (export.py:116-125) -> list of (N,2) int64 numpy arrays (row, col)."""
+    def keypoints_async(self, heat):
+        """box_nms + threshold + nonzero (export.py:116-125) enqueued on the current stream; the keypoint lists are
+        copied to pinned host memory asynchronously.  Returns a handle for ``keypoints_wait``."""
         ctx = self.model.native()
         NI, H, W = heat.shape
         max_kp = min(H * W, 16384)
-        while True:
-            r = ctx.box_nms(heat, float(self.dh["nms"]), 0.1, float(self.dh["det_thresh"]), int(self.dh["top_k"]),
-                            det_thresh=float(self.dh["det_thresh"]), want_map=False, max_kp=max_kp)
-            counts = r["kp_count"].cpu().numpy()
-            if counts.max(initial=0) <= max_kp:
-                break
-            max_kp = int(counts.max())
-        kp = r["kp"].cpu().numpy()
-        return [kp[i, :counts[i]].astype(np.int64) for i in range(NI)]
+        r = ctx.box_nms(heat, float(self.dh["nms"]), 0.1, float(self.dh["det_thresh"]), int(self.dh["top_k"]),
+                        det_thresh=float(self.dh["det_thresh"]), want_map=False, max_kp=max_kp)
+        kp_h = torch.empty(r["kp"].shape, dtype=torch.int32, pin_memory=True)
+        cnt_h = torch.empty(r["kp_count"].shape, dtype=torch.int32, pin_memory=True)
+        kp_h.copy_(r["kp"], non_blocking=True)
+        cnt_h.copy_(r["kp_count"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return {"heat": heat, "kp": kp_h, "count": cnt_h, "event": ev, "max_kp": max_kp, "dev": r}
+
+    def keypoints_wait(self, handle):
+        """-> list of (N,2) int64 numpy arrays (row, col), row-major order like torch.nonzero."""
+        handle["event"].synchronize()
+        counts = handle["count"].numpy()
+        if counts.max(initial=0) > handle["max_kp"]:      # rare: more keypoints than the buffer, redo with the true size
+            ctx = self.model.native()
+            r = ctx.box_nms(handle["heat"], float(self.dh["nms"]), 0.1, float(self.dh["det_thresh"]), int(self.dh["top_k"]),
+                            det_thresh=float(self.dh["det_thresh"]), want_map=False, max_kp=int(counts.max()))
+            kp = r["kp"].cpu().numpy()
+        else:
+            kp = handle["kp"].numpy()
+        return [kp[i, :counts[i]].astype(np.int64) for i in range(len(counts))]
+
+    @torch.no_grad()
+    def keypoints(self, heat):
+        return self.keypoints_wait(self.keypoints_async(heat))
 
     def __call__(self, images, homographies=None, enable_HA=True, first_index=0):
         heat, _ = self.heatmaps(images, homographies, enable_HA, first_index)
@@ -152,18 +170,34 @@ class ExportDetections:
         os.makedirs(out, exist_ok=True)
         return out
 
-    def _flush(self, group, index):
-        if not group:
-            return
+    def _launch(self, group, index):
+        """Enqueue the whole GPU pass for a group of images; returns a handle (nothing is synchronised)."""
         images = torch.cat([g[1] for g in group], dim=0)
-        kps = self.engine(images, enable_HA=self.enable_HA, first_index=index)
-        for (path, _), kp in zip(group, kps):
+        heat, _ = self.engine.heatmaps(images, enable_HA=self.enable_HA, first_index=index)
+        return [g[0] for g in group], self.engine.keypoints_async(heat)
+
+    def _finish(self, pending):
+        paths, handle = pending
+        for path, kp in zip(paths, self.engine.keypoints_wait(handle)):
             np.save(path, kp)
 
     @torch.no_grad()
     def homography_adaptation(self):
+        """Same loop as export.py:82-129, software-pipelined: while the GPU works on group k the host saves group k-1."""
         per_launch = int(self.config["homography_adaptation"].get("images_per_launch", 1))
-        group, done = [], 0
+        group, done, pending = [], 0, None
+
+        def flush():
+            nonlocal group, done, pending
+            if not group:
+                return
+            cur = self._launch(group, done)
+            if pending is not None:
+                self._finish(pending)
+            pending = cur
+            done += len(group)
+            group = []
+
         for data in tqdm(self.dataloader, desc="Exporting detections", colour="green"):
             name = data["name"][0]
             save_path = Path(self.output_dir, f"{name}.npy")
@@ -171,15 +205,13 @@ class ExportDetections:
                 continue
             image = move_to_device(data["raw"]["image"], self.device)
             if group and group[0][1].shape != image.shape:
-                self._flush(group, done)
-                done += len(group)
-                group = []
+                flush()
             group.append((save_path, image))
             if len(group) >= per_launch:
-                self._flush(group, done)
-                done += len(group)
-                group = []
-        self._flush(group, done)
+                flush()
+        flush()
+        if pending is not None:
+            self._finish(pending)
 
 
 def _np(t):
