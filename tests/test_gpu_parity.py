@@ -384,3 +384,23 @@ def test_export_batching_and_streams_are_transparent(P, tmp_path, monkeypatch):
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
     assert all(len(a) > 0 for a in outs[0])
+
+
+def test_sparse_descriptors_bilinear_and_bicubic_vs_torch(ctx):
+    """spn_sample_descriptors vs F.interpolate(..., align_corners=False) + F.normalize evaluated densely on the CPU:
+    bicubic is the reference's mode (heads.py:65-66); bilinear is the north_star's 'bilinear descriptor sampling'."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(3)
+    raw = torch.from_numpy(rng.randn(2, 256, 15, 20).astype(np.float32))
+    pts = np.stack([rng.randint(0, 120, 200), rng.randint(0, 160, 200)], 1).astype(np.int32)
+    pts[:6] = [[0, 0], [0, 159], [119, 0], [119, 159], [3, 4], [4, 3]]
+    kp = torch.from_numpy(np.stack([pts, pts[::-1].copy()])).cuda().contiguous()
+    cnt = torch.tensor([200, 150], dtype=torch.int32, device="cuda")
+    for mode in ("bicubic", "bilinear"):
+        dense = F.normalize(F.interpolate(raw, scale_factor=8, mode=mode, align_corners=False), p=2, dim=1).numpy()
+        got = ctx.sample_descriptors(raw.cuda(), 8, kp, cnt, interp=mode).cpu().numpy()
+        for b, n in ((0, 200), (1, 150)):
+            p = kp[b, :n].cpu().numpy()
+            want = dense[b][:, p[:, 0], p[:, 1]].T
+            assert rel_err(got[b, :n], want) < STRICT, mode
+        assert np.all(got[1, 150:] == 0)        # slots beyond kp_count stay zero
