@@ -399,6 +399,10 @@ int launch_conv_tc(spn_ctx* ctx, int layer, int mode, const void* in, void* out,
   TcState* st = tc_state(ctx);
   const SpnLayer& L = ctx->layers[layer];
   const int bf = mode == SPN_MODE_BF16 ? 1 : 0;
+  if (L.ks == 3 && out_mode == 0) {  // 3x3 layers: horizontal taps folded into N (conv_fold.cu) unless SPN_TC_FOLD=0
+    const char* fold = getenv("SPN_TC_FOLD");
+    if (!fold || atoi(fold)) return spn_launch_conv_fold(ctx, layer, mode, in, out, n_img, H, W, relu, pool, s);
+  }
   if (!L.w16[bf] || !st->bias_pad[layer]) { spn_set_error("layer %d has no tensor-core weights", layer); return SPN_E_STATE; }
   SPN_REQUIRE(L.cin % 64 == 0, "tensor-core conv needs Cin %% 64 == 0 (layer %d has %d)", layer, L.cin);
   int rc = get_encode(st);
@@ -542,10 +546,16 @@ int spn_tc_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float
     SPN_CUDA(cudaMalloc(&L.w16[bf], n16 * 2));
     SPN_CUDA(cudaMemcpy(L.w16[bf], img.data(), n16 * 2, cudaMemcpyHostToDevice));
   }
-  return SPN_OK;
+  return spn_fold_pack_layer(ctx, layer, h_wfold, h_bfold);
 }
 
 const float* spn_tc_bias(spn_ctx* ctx, int layer) { return tc_state(ctx)->bias_pad[layer]; }
+
+void* spn_tc_encode_fn(spn_ctx* ctx) {
+  TcState* st = tc_state(ctx);
+  if (get_encode(st) != SPN_OK) return nullptr;
+  return (void*)st->encode;
+}
 
 // Encoder over `n_slots` forwards.  d_hinv == nullptr: slot i is image i (plain forward).  Otherwise slot =
 // src*(n_h+1)+j is image `src` warped by homography j-1 (j == 0: the image itself) and the warp is fused in.

@@ -74,6 +74,7 @@ extern "C" int spn_destroy(spn_ctx* ctx) {
     if (L.w32) cudaFree(L.w32);
     if (L.bias) cudaFree(L.bias);
     for (auto& p : L.w16) if (p) cudaFree(p);
+    for (auto& p : L.w16f) if (p) cudaFree(p);
   }
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->aux) cudaFree(ctx->aux);

@@ -16,6 +16,7 @@ struct SpnLayer {
   float* w32 = nullptr;    // [cin][ks*ks][cout_pad] fp32, BN folded
   float* bias = nullptr;   // [cout_pad] fp32, BN folded
   void* w16[2] = {nullptr, nullptr};  // tcgen05 operand-B images (fp16, bf16), see conv_tc.cu
+  void* w16f[2] = {nullptr, nullptr}; // same for the kx-folded 3x3 kernel (N = 192), see conv_fold.cu
 };
 
 struct SpnProfRec {
@@ -104,6 +105,10 @@ int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_l
 int spn_tc_descriptor_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw, cudaStream_t s);
 void spn_tc_destroy(spn_ctx* ctx);
 const float* spn_tc_bias(spn_ctx* ctx, int layer);
+void* spn_tc_encode_fn(spn_ctx* ctx);  // cuTensorMapEncodeTiled, or nullptr (error set)
+int spn_fold_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float* h_bfold);
+int spn_launch_conv_fold(spn_ctx* ctx, int layer, int mode, const void* in, void* out, int n_img, int H, int W, bool relu,
+                         bool pool, cudaStream_t s);
 int spn_tc_encoder_slots(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots,
                          int H, int W, int mode, cudaStream_t s);
 int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots, int H,
