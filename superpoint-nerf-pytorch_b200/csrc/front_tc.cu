@@ -50,6 +50,7 @@ struct FrontParams {
   int n_h;               // homographies per source image (slot = src * (n_h + 1) + j, j == 0 is the identity)
   int slot_begin, n_slots;
   int H, W, tiles_x, tiles_y;
+  unsigned long long magic_tpi, magic_tx;   // fast_div magics for tiles_per_img and tiles_x
   int is_bf16;
   const void* w1img;     // operand-B image of block_1 (taps + bias rows)
   const void* w2img;     // operand-B image of block_2 (72 KB) followed by its 2 KB bias block
@@ -186,22 +187,24 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
   } else if (warp >= 10) {
     // ===================== P: warped patch + im2col operand of block_1 =====================
     const int pt = threadIdx.x - 320;  // 0..255
+    float hm[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    int hm_slot = -1;
     int i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       const int b = i % kNA1;
       const uint32_t ph = (uint32_t)(i / kNA1) & 1u;
-      const int ls = t / tiles_per_img, rr = t - ls * tiles_per_img;
-      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      const int ls = fast_div(t, p.magic_tpi), rr = t - ls * tiles_per_img;
+      const int ty = fast_div(rr, p.magic_tx), tx = rr - ty * p.tiles_x;
       const int slot = p.slot_begin + ls;
       const int src = p.hinv ? slot / (p.n_h + 1) : slot;
       const int j = p.hinv ? slot - src * (p.n_h + 1) : 0;
       const float* img = p.images + (size_t)src * p.H * p.W;
       mbar_wait(&bar_a1_empty[b], ph ^ 1u);  // MMA1 of tile i-3 has consumed A1[b] (and patch_s[b] long before)
-      float hm[9];
-      if (j > 0) {  // same 36 bytes for every thread of the tile: L1 broadcast
+      if (j > 0 && slot != hm_slot) {  // warp-uniform; a CTA's consecutive tiles mostly belong to the same slot
         const float* hp = p.hinv + ((size_t)src * p.n_h + (j - 1)) * 9;
 #pragma unroll
         for (int k = 0; k < 9; ++k) hm[k] = __ldg(hp + k);
+        hm_slot = slot;
       }
       // 1. the 12 x 20 patch of the warped image around the tile (zero outside the frame = block_1's padding)
       for (int s = pt; s < kQH * kQW; s += kPThreads) {
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
           } else {
             float sx, sy;
             apply_h(hm, (float)x, (float)y, sx, sy);
-            v = bilinear_zero(img, sx, sy, p.H, p.W);
+            v = bilinear_zero_nb(img, sx, sy, p.H, p.W);
           }
         }
         patch_s[b][s] = to16(v, p.is_bf16);
@@ -291,8 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       const int acc = i & 1;
       const uint32_t aph = (uint32_t)(i >> 1) & 1u;
-      const int ls = t / tiles_per_img, rr = t - ls * tiles_per_img;
-      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      const int ls = fast_div(t, p.magic_tpi), rr = t - ls * tiles_per_img;
+      const int ty = fast_div(rr, p.magic_tx), tx = rr - ty * p.tiles_x;
       const int y = ty * kTH + g, x = tx * kTW + r;
       mbar_wait(&bar_d2_full[acc], aph);
       tc_fence_after();
@@ -341,6 +344,8 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
   memset(&p, 0, sizeof(p));
   p.images = d_images; p.hinv = d_hinv; p.n_h = n_h; p.slot_begin = slot_begin; p.n_slots = n_slots;
   p.H = H; p.W = W; p.tiles_x = spn_cdiv(W, kTW); p.tiles_y = spn_cdiv(H, kTH); p.is_bf16 = bf;
+  p.magic_tpi = fast_div_magic(p.tiles_x * p.tiles_y); p.magic_tx = fast_div_magic(p.tiles_x);
+  SPN_REQUIRE((long long)n_slots * p.tiles_x * p.tiles_y * (p.tiles_x * p.tiles_y) < (1ll << 40), "too many tiles for one launch");
   p.w1img = w1img; p.w2img = L2.w16[bf];
   p.out = d_out;
   const size_t dyn = (size_t)kW2Bytes + kW1Bytes + kNA1 * kA1Bytes + kOnesBytes + (size_t)kStages * kStageBytes + 1024;

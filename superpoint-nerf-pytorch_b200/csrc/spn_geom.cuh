@@ -38,4 +38,31 @@ __device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, fl
   return v;
 }
 
+// Branch-free variant for latency-critical producers: the four taps are always loaded from clamped addresses and a
+// tap outside the image gets weight 0 (same value as bilinear_zero, no divergent control flow).
+__device__ __forceinline__ float bilinear_zero_nb(const float* __restrict__ img, float sx, float sy, int H, int W) {
+  const bool ok = sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H;  // also rejects NaN/inf
+  const float cx = ok ? sx : 0.f, cy = ok ? sy : 0.f;
+  const float fx = floorf(cx), fy = floorf(cy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const float wx1 = cx - fx, wy1 = cy - fy;
+  const float wx0 = (fx + 1.f) - cx, wy0 = (fy + 1.f) - cy;
+  const float mx0 = (x0 >= 0 && ok) ? wx0 : 0.f, mx1 = (x0 + 1 < W && ok) ? wx1 : 0.f;
+  const float my0 = (y0 >= 0) ? wy0 : 0.f, my1 = (y0 + 1 < H) ? wy1 : 0.f;
+  const int xa = max(x0, 0), xb = min(x0 + 1, W - 1), ya = max(y0, 0), yb = min(y0 + 1, H - 1);
+  const float v00 = __ldg(&img[(size_t)ya * W + xa]), v01 = __ldg(&img[(size_t)ya * W + xb]);
+  const float v10 = __ldg(&img[(size_t)yb * W + xa]), v11 = __ldg(&img[(size_t)yb * W + xb]);
+  float v = v00 * (mx0 * my0);
+  v = fmaf(v01, mx1 * my0, v);
+  v = fmaf(v10, mx0 * my1, v);
+  v = fmaf(v11, mx1 * my1, v);
+  return v;
+}
+
+// Exact t / d for 0 <= t, t * d < 2^40, with m = ceil(2^40 / d) computed on the host (fast_div_magic).
+__device__ __forceinline__ int fast_div(int t, unsigned long long m) {
+  return (int)(((unsigned long long)(unsigned)t * m) >> 40);
+}
+inline unsigned long long fast_div_magic(int d) { return ((1ull << 40) + (unsigned long long)d - 1) / (unsigned long long)d; }
+
 }  // namespace spngeom
