@@ -320,7 +320,9 @@ def run_native(args):
                 "traffic": (tpf * fwd_per_launch) if tpf else None, "traffic_unit": "bytes per launch (ncu dram read+write)",
                 "algorithmic_flops_per_launch": (LAYER_FLOPS["backbone.block_2"] + (LAYER_FLOPS["backbone.block_1"]
                                                  if "backbone.block_1" not in prof else 0.0)) * fwd_per_launch,
-                "ms_per_launch": dom["ms_per_launch"], "kernel": "backbone.block_2 3x3 conv 64->64 @240x320 (implicit GEMM M=pixels N=64 K=576)",
+                "ms_per_launch": dom["ms_per_launch"], "kernel": ("front_tc_kernel = homography warp + block_1 (1->64) + block_2 (64->64, ReLU, 2x2 pool) fused; implicit GEMM "
+                           "M=pixels N=64 K=576 (+K=16 for block_1) @240x320") if args.precision != "fp32" else
+                          "conv_fp32_kernel block_2 (strict FFMA path; tensor peak shown for scale only)",
                 "peak_source": f"{pk_kind} bf16_tflops_sustained", "share_of_step": (prof["backbone.block_2"][0] / total_kernel_ms)
                 if total_kernel_ms else None}
     line = {"metric": "pseudo-label img/s (240x320, 100 H)", "value": value, "unit": "img/s", "n_gpus": world,
