@@ -119,3 +119,24 @@ def test_fused_front_end_matches_unfused(monkeypatch):
         print(f"{NI}x{H}x{W}: fused-vs-unfused rel err plain {e1:.2e}  ha {e2:.2e}")
         assert e1 < 8e-3 and e2 < 8e-3  # two different fp16 roundings of block_1; each is gated against fp32 elsewhere
         assert torch.equal(part, fused_ha[2:B - 1])
+
+
+@pytest.mark.parametrize("shape", [(1, 480, 640), (3, 120, 160), (2, 72, 200)])
+def test_forward_fast_other_sizes_vs_oracle(shape):
+    """BASELINE config 3 size (480x640) and sizes whose feature maps do not fill the 8x16 / 8x14 tiles."""
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    B, H, W = shape
+    sd = O.make_state_dict("superpoint", seed=33, logit_gain=5.0)
+    c = copy.deepcopy(SP_MODEL)
+    c["precision"] = "f16"
+    c["dense_desc"] = False
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    x = torch.from_numpy(np.stack([smooth_image(H, W, 90 + i) for i in range(B)])[:, None])
+    want = O.model_forward(sd, x, SP_MODEL, dense_desc=False)
+    got = m(x.cuda())
+    e1 = rel_err(got["detector_output"]["logits"].cpu().numpy(), want["detector_output"]["logits"].numpy())
+    e2 = rel_err(got["detector_output"]["prob_heatmap"].cpu().numpy(), want["detector_output"]["prob_heatmap"].numpy())
+    e3 = rel_err(got["descriptor_output"]["desc_raw"].cpu().numpy(), want["descriptor_output"]["desc_raw"].numpy())
+    print(f"{shape}: logits {e1:.2e} prob {e2:.2e} desc_raw {e3:.2e}")
+    assert e1 < FAST and e2 < FAST and e3 < FAST, (e1, e2, e3)
