@@ -73,8 +73,16 @@ def load_library():
     with _lock:
         if _lib is None:
             if not _LIB_PATH.exists():
-                raise NativeError(f"{_LIB_PATH} not found: build it with `python superpoint-nerf-pytorch_b200/build.py` "
-                                  "(there is no CPU/PyTorch fallback)")
+                # build on demand (nvcc, in-tree); still no fallback: without nvcc or on failure this raises
+                try:
+                    import importlib.util
+                    spec = importlib.util.spec_from_file_location("spn_build", _HERE / "build.py")
+                    mod = importlib.util.module_from_spec(spec)
+                    spec.loader.exec_module(mod)
+                    mod.build()
+                except Exception as e:
+                    raise NativeError(f"{_LIB_PATH} not found and building it failed ({e}); build it with "
+                                      "`python superpoint-nerf-pytorch_b200/build.py` (there is no CPU/PyTorch fallback)")
             lib = C.CDLL(str(_LIB_PATH))
             for name, (res, args) in PROTOTYPES.items():
                 fn = getattr(lib, name)
