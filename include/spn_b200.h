@@ -149,6 +149,13 @@ typedef struct spn_homography_params {
 SPN_API int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params* params, uint64_t seed, uint64_t first_index,
                             int count, int H, int W, float* d_h, float* d_hinv, spn_stream stream);
 
+/* Loader pre-processing of one decoded grayscale image (data/COCO.py:66-76 ratio_preserving_resize + the /255 of
+ * COCO.py:135; data/HPatches.py:64-72): bilinear resize to new_h x new_w (align_corners=False, as kornia.resize ->
+ * F.interpolate), centre crop at (crop_top, crop_left) to H x W (zero padded when the resized image is smaller, as
+ * torchvision center_crop does), divide by `divisor`.  d_src [H0][W0] uint8 (src_is_u8 != 0) or fp32; d_out [H][W]. */
+SPN_API int spn_resize_crop(spn_ctx* ctx, const void* d_src, int src_is_u8, int H0, int W0, int new_h, int new_w,
+                            int crop_top, int crop_left, int H, int W, float divisor, float* d_out, spn_stream stream);
+
 /* 3x3 inverse, fp32, batched (export.py:49 torch.inverse). d_in/d_out [count][9]. */
 SPN_API int spn_invert3x3(spn_ctx* ctx, const float* d_in, int count, float* d_out, spn_stream stream);
 

@@ -113,6 +113,20 @@ def erosion(tensor, kernel, structuring_element=None, origin=None, border_type="
     return out
 
 
+def resize(input, size, interpolation="bilinear", align_corners=None, side="short", antialias=False):
+    """kornia 0.7.0 geometry.transform.resize for an explicit (h, w) size (call sites: data/COCO.py:74,
+    data/HPatches.py:70): promote to BCHW, F.interpolate(size, mode, align_corners, antialias), restore the rank."""
+    if not isinstance(size, (tuple, list)):
+        raise NotImplementedError("restated for explicit (h, w) sizes only (the reference's call sites)")
+    shape = input.shape
+    x = input.reshape((1,) * (4 - input.dim()) + tuple(shape)) if input.dim() < 4 else input
+    h, w = int(size[0]), int(size[1])
+    if tuple(x.shape[-2:]) == (h, w):
+        return input
+    out = F.interpolate(x, size=(h, w), mode=interpolation, align_corners=align_corners, antialias=antialias)
+    return out.reshape(tuple(shape[:-2]) + (h, w))
+
+
 def install(exper_path: str = "/tmp/spn_exper", data_path: str = "/tmp/spn_data", ckpt_path: str = "/tmp/spn_ckpt") -> None:
     """Register stub ``kornia`` / ``matplotlib`` / ``superpoint.settings`` modules so the unmodified
     reference imports.  Build-container use only."""
@@ -121,6 +135,7 @@ def install(exper_path: str = "/tmp/spn_exper", data_path: str = "/tmp/spn_data"
     kgt = types.ModuleType("kornia.geometry.transform")
     km = types.ModuleType("kornia.morphology")
     kgt.warp_perspective = warp_perspective
+    kgt.resize = resize
     km.erosion = erosion
     k.geometry, kg.transform, k.morphology = kg, kgt, km
     for name, mod in (("kornia", k), ("kornia.geometry", kg), ("kornia.geometry.transform", kgt), ("kornia.morphology", km)):

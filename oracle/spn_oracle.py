@@ -423,3 +423,38 @@ def sparse_descriptors(desc_raw, pts, grid=8):
             acc = acc + row * float(wy[a])
         out[n] = acc / acc.norm().clamp_min(1e-12)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# Loader pre-processing: data/COCO.py:66-76 + :135, data/HPatches.py:74-100
+# --------------------------------------------------------------------------------------------
+
+def ratio_preserving_resize(image, target, normalize=True):
+    """COCO.ratio_preserving_resize (data/COCO.py:66-76) on a decoded grayscale image (H0,W0) fp32 [0,255], then the
+    "/= 255." of COCO.py:135."""
+    import torchvision.transforms.functional as TF
+
+    target_size = torch.as_tensor(list(target), dtype=torch.int32)
+    scales = torch.divide(target_size, torch.as_tensor(image.shape, dtype=torch.float32))
+    new_size = (torch.as_tensor(image.shape[:2], dtype=torch.float32) * torch.max(scales)).to(torch.int32)
+    out = K.resize(image, size=[new_size[0], new_size[1]], interpolation="bilinear", align_corners=False)
+    out = TF.center_crop(out, output_size=[int(target_size[0]), int(target_size[1])])
+    return out / 255.0 if normalize else out
+
+
+def adapt_homography_to_resize(homography, image_shape, warped_image_shape, target):
+    """HPatches.adapt_homography_to_resize (data/HPatches.py:74-100)."""
+    source_size = torch.as_tensor(image_shape, dtype=torch.float32)
+    source_warped_size = torch.as_tensor(warped_image_shape, dtype=torch.float32)
+    target_size = torch.as_tensor(list(target), dtype=torch.float32)
+    s = torch.max(torch.divide(target_size, source_size))
+    up = torch.diag(torch.stack([1.0 / s, 1.0 / s, torch.tensor(1.0)]))
+    ws = torch.max(torch.divide(target_size, source_warped_size))
+    down = torch.diag(torch.stack([ws, ws, torch.tensor(1.0)]))
+    t = torch.eye(3)
+    t[0, -1] = ((source_size[1] * s - target_size[1]) / torch.tensor(2.0)).to(torch.int32)
+    t[1, -1] = ((source_size[0] * s - target_size[0]) / torch.tensor(2.0)).to(torch.int32)
+    wt = torch.eye(3)
+    wt[0, -1] = -((source_warped_size[1] * ws - target_size[1]) / torch.tensor(2.0)).to(torch.int32)
+    wt[1, -1] = -((source_warped_size[0] * ws - target_size[0]) / torch.tensor(2.0)).to(torch.int32)
+    return wt @ down @ torch.as_tensor(homography, dtype=torch.float32) @ up @ t

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "spn_warp_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "spn_ha_aggregate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "spn_sample_homographies": (_i, [_vp, C.POINTER(HomographyParams), C.c_uint64, C.c_uint64, _i, _i, _i, _vp, _vp, _vp]),
+    "spn_resize_crop": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "spn_invert3x3": (_i, [_vp, _vp, _i, _vp, _vp]),
     "spn_launch_count": (C.c_int64, [_vp]),
     "spn_profile_enable": (_i, [_vp, _i]),
@@ -305,6 +306,16 @@ class Context:
         self._call("spn_sample_homographies", self.handle, C.byref(p), C.c_uint64(seed), C.c_uint64(first_index), count, H, W,
                    _ptr(h), _ptr(hinv), _stream())
         return h, hinv
+
+    def resize_crop(self, src: torch.Tensor, new_h, new_w, crop_top, crop_left, H, W, divisor=255.0):
+        """src (H0,W0) uint8 or fp32 CUDA -> (H,W) fp32: bilinear resize + centre crop + /divisor (loader pre-processing)."""
+        src = _dense(src)
+        if not (src.is_cuda and src.dim() == 2 and src.dtype in (torch.uint8, torch.float32)):
+            raise NativeError("resize_crop: src must be a 2-D uint8/float32 CUDA tensor")
+        out = torch.empty((H, W), dtype=torch.float32, device=src.device)
+        self._call("spn_resize_crop", self.handle, _ptr(src), int(src.dtype == torch.uint8), src.shape[0], src.shape[1], int(new_h),
+                   int(new_w), int(crop_top), int(crop_left), int(H), int(W), C.c_float(divisor), _ptr(out), _stream())
+        return out
 
     def invert3x3(self, m):
         m = _dense(m)

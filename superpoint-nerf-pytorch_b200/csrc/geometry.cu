@@ -373,7 +373,46 @@ __global__ void invert3x3_kernel(const float* __restrict__ in, int count, float*
   for (int k = 0; k < 9; ++k) out[(size_t)i * 9 + k] = o[k];
 }
 
+// Loader pre-processing (data/COCO.py:66-76, data/HPatches.py:64-72): bilinear resize (align_corners=False, no
+// antialias, i.e. F.interpolate as kornia.resize calls it) + centre crop (zero pad if the resized image is smaller)
+// + division by 255, fused; source is the decoded grayscale image as uint8 or float32.
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_crop_kernel(const T* __restrict__ src, int H0, int W0, int nh, int nw, int top, int left, int H, int W,
+                   float divisor, float* __restrict__ out) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= W || y >= H) return;
+  const int ry = y + top, rx = x + left;  // coordinates in the resized image
+  float v = 0.f;
+  if (ry >= 0 && ry < nh && rx >= 0 && rx < nw) {
+    const float sy = fmaxf(((float)H0 / (float)nh) * ((float)ry + 0.5f) - 0.5f, 0.f);
+    const float sx = fmaxf(((float)W0 / (float)nw) * ((float)rx + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < H0 - 1 ? 1 : 0), x1 = x0 + (x0 < W0 - 1 ? 1 : 0);
+    const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+    const float v00 = (float)src[(size_t)y0 * W0 + x0], v01 = (float)src[(size_t)y0 * W0 + x1];
+    const float v10 = (float)src[(size_t)y1 * W0 + x0], v11 = (float)src[(size_t)y1 * W0 + x1];
+    v = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+  }
+  out[(size_t)y * W + x] = v / divisor;
+}
+
 }  // namespace
+
+extern "C" int spn_resize_crop(spn_ctx* ctx, const void* d_src, int src_is_u8, int H0, int W0, int new_h, int new_w,
+                               int crop_top, int crop_left, int H, int W, float divisor, float* d_out, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_src && d_out, "spn_resize_crop: null pointer");
+  SPN_REQUIRE(H0 > 0 && W0 > 0 && new_h > 0 && new_w > 0 && H > 0 && W > 0 && divisor != 0.f, "spn_resize_crop: bad shape");
+  dim3 grid(spn_cdiv(W, 32), spn_cdiv(H, 8));
+  if (src_is_u8)
+    resize_crop_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)d_src, H0, W0, new_h, new_w, crop_top,
+                                                                         crop_left, H, W, divisor, d_out);
+  else
+    resize_crop_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)d_src, H0, W0, new_h, new_w, crop_top, crop_left,
+                                                                       H, W, divisor, d_out);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}
 
 extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H,
                               int W, int margin, float* d_warped, uint8_t* d_mask, spn_stream stream) {

@@ -235,6 +235,32 @@ def main():
     layout["des_desc_at_pts"] = des["desc"][ys, xs]          # (32,256) from the (H,W,256) layout
     layout["des_warped_desc_at_pts"] = des["warped_desc"][ys, xs]
     np.savez_compressed(OUT / "hpatches_export.npz", **layout)
+    # ---- 7. loader pre-processing: COCO.ratio_preserving_resize, HPatches.adapt_homography_to_resize
+    from superpoint.data.COCO import COCO
+    from superpoint.data.HPatches import HPatches
+    pre = {}
+    rngp = np.random.RandomState(12)
+    cases = [((96, 128), (48, 64)), ((107, 160), (48, 64)), ((94, 125), (48, 64)), ((160, 120), (48, 64)), ((83, 125), (60, 80)),
+             ((61, 80), (60, 80)), ((50, 70), (48, 64))]
+    for k, (src, tgt) in enumerate(cases):
+        ds = object.__new__(COCO)
+        ds.config = {"preprocessing": {"resize": list(tgt)}}
+        u8 = rngp.randint(0, 256, size=src).astype(np.uint8)
+        out = ds.ratio_preserving_resize(torch.from_numpy(u8).to(torch.float32)) / 255.0
+        pre[f"img{k}"] = u8
+        pre[f"tgt{k}"] = np.array(tgt)
+        pre[f"out{k}"] = out.numpy()
+    pre["n"] = np.array(len(cases))
+    hp = object.__new__(HPatches)
+    hp.config = {"preprocessing": {"resize": [240, 320]}}
+    hp.device = "cpu"
+    Hs_in = rngp.randn(3, 3).astype(np.float32) * 0.01 + np.eye(3, dtype=np.float32)
+    hom = {"homography": torch.from_numpy(Hs_in), "image_shape": torch.tensor([480.0, 640.0]),
+           "warped_image_shape": torch.tensor([427.0, 600.0])}
+    pre["h_in"] = Hs_in
+    pre["h_out"] = hp.adapt_homography_to_resize(hom).numpy()
+    np.savez_compressed(OUT / "preprocess.npz", **pre)
+
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

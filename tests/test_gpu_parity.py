@@ -404,3 +404,22 @@ def test_sparse_descriptors_bilinear_and_bicubic_vs_torch(ctx):
             want = dense[b][:, p[:, 0], p[:, 1]].T
             assert rel_err(got[b, :n], want) < STRICT, mode
         assert np.all(got[1, 150:] == 0)        # slots beyond kp_count stay zero
+
+
+def test_preprocessing_kernel_vs_reference(ctx, golden):
+    """spn_resize_crop (uint8 and fp32 sources) vs the reference loader's ratio_preserving_resize + /255."""
+    from superpoint_nerf_pytorch_b200.data.preprocessing import ratio_preserving_resize
+    g = golden("preprocess.npz")
+    for k in range(int(g["n"])):
+        u8 = torch.from_numpy(g[f"img{k}"])
+        tgt = tuple(int(v) for v in g[f"tgt{k}"])
+        for src in (u8.cuda(), u8.to(torch.float32).cuda(), u8):   # uint8 on device, fp32 on device, uint8 on host
+            out = ratio_preserving_resize(src, tgt).cpu().numpy()
+            assert out.shape == tgt
+            assert np.abs(out - g[f"out{k}"]).max() < 2e-6, k
+    # BASELINE-size case against the oracle
+    rng = np.random.RandomState(0)
+    big = torch.from_numpy(rng.randint(0, 256, size=(427, 640)).astype(np.uint8))
+    want = O.ratio_preserving_resize(big.to(torch.float32), (240, 320)).numpy()
+    got = ratio_preserving_resize(big.cuda(), (240, 320)).cpu().numpy()
+    assert np.abs(got - want).max() < 2e-6

@@ -107,3 +107,24 @@ def test_shard_plan():
             allidx = sorted(i for p in parts for i in p)
             assert allidx == list(range(n))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_preprocessing_host_side_matches_reference(golden):
+    from superpoint_nerf_pytorch_b200.data.preprocessing import adapt_homography_to_resize, resize_geometry
+    import torchvision.transforms.functional as TF
+    g = golden("preprocess.npz")
+    h = adapt_homography_to_resize(g["h_in"], [480.0, 640.0], [427.0, 600.0], (240, 320))
+    assert np.array_equal(h.numpy(), g["h_out"])
+    # crop geometry == what torchvision's center_crop does on the resized image (incl. the zero-padded case)
+    for src, tgt in [((96, 128), (48, 64)), ((107, 160), (48, 64)), ((160, 120), (48, 64)), ((61, 80), (60, 80)), ((50, 70), (48, 64)),
+                     ((427, 640), (240, 320)), ((333, 500), (240, 320)), ((30, 90), (48, 64))]:
+        nh, nw, top, left = resize_geometry(src, tgt)
+        probe = torch.arange(nh * nw, dtype=torch.float32).reshape(nh, nw) + 1.0
+        want = TF.center_crop(probe, list(tgt))
+        got = torch.zeros(tgt)
+        for y in range(tgt[0]):
+            for x in range(tgt[1]):
+                ry, rx = y + top, x + left
+                if 0 <= ry < nh and 0 <= rx < nw:
+                    got[y, x] = probe[ry, rx]
+        assert torch.equal(got, want), (src, tgt)

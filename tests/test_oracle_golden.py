@@ -123,3 +123,14 @@ def test_ha_export_matches_reference(golden):
     kp = g["keypoints"]
     lin = kp[:, 0] * 160 + kp[:, 1]
     assert kp.ndim == 2 and kp.shape[1] == 2 and np.all(np.diff(lin) > 0)
+
+
+def test_preprocessing_matches_reference(golden):
+    """COCO.ratio_preserving_resize (+ /255) and HPatches.adapt_homography_to_resize."""
+    g = golden("preprocess.npz")
+    for k in range(int(g["n"])):
+        img = torch.from_numpy(g[f"img{k}"]).to(torch.float32)
+        out = O.ratio_preserving_resize(img, tuple(g[f"tgt{k}"]))
+        assert np.array_equal(out.numpy(), g[f"out{k}"]), k
+    h = O.adapt_homography_to_resize(g["h_in"], [480.0, 640.0], [427.0, 600.0], (240, 320))
+    assert np.array_equal(h.numpy(), g["h_out"])
