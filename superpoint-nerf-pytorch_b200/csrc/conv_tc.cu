@@ -546,7 +546,9 @@ int spn_tc_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float
     SPN_CUDA(cudaMalloc(&L.w16[bf], n16 * 2));
     SPN_CUDA(cudaMemcpy(L.w16[bf], img.data(), n16 * 2, cudaMemcpyHostToDevice));
   }
-  return spn_fold_pack_layer(ctx, layer, h_wfold, h_bfold);
+  int rc = spn_fold_pack_layer(ctx, layer, h_wfold, h_bfold);
+  if (rc) return rc;
+  return spn_head_pack_layer(ctx, layer, h_wfold, h_bfold);
 }
 
 const float* spn_tc_bias(spn_ctx* ctx, int layer) { return tc_state(ctx)->bias_pad[layer]; }
@@ -605,6 +607,16 @@ int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_l
   int rc;
   if ((rc = launch_conv_tc(ctx, SPN_L_CONVPA, mode, ctx->feat, head, B, H / 8, W / 8, true, false, 0, s))) return rc;
   return launch_conv_tc(ctx, SPN_L_CONVPB, mode, head, d_logits, B, H / 8, W / 8, false, false, 1, s);
+}
+
+// convPa, then convPb + softmax + depth-to-space + mask in one kernel (head_tc.cu)
+int spn_tc_detector_head_fused(spn_ctx* ctx, int B, int H, int W, int mode, const uint8_t* d_mask, float* d_logits, float* d_prob,
+                               cudaStream_t s) {
+  const TcPlan pl = tc_plan(B, H, W);
+  char* head = ctx->ws + pl.a + pl.b + pl.feat;
+  int rc;
+  if ((rc = launch_conv_tc(ctx, SPN_L_CONVPA, mode, ctx->feat, head, B, H / 8, W / 8, true, false, 0, s))) return rc;
+  return spn_launch_head_tc(ctx, mode, head, B, H / 8, W / 8, d_mask, d_logits, d_prob, s);
 }
 
 int spn_tc_descriptor_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw, cudaStream_t s) {

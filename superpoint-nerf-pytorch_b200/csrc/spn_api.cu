@@ -250,6 +250,9 @@ extern "C" int spn_detector_head_forward(spn_ctx* ctx, int B, int H, int W, int 
     if ((rc = spn_conv_fp32(ctx, SPN_L_CONVPA, (const float*)ctx->feat, A, B, Hc, Wc, true, false, s))) return rc;
     if ((rc = spn_conv_fp32(ctx, SPN_L_CONVPB, A, logits, B, Hc, Wc, false, false, s))) return rc;
   } else {
+    const char* nofuse = getenv("SPN_TC_NOHEADFUSE");
+    if (!(nofuse && atoi(nofuse)) && ctx->layers[SPN_L_CONVPB].w16f[mode == SPN_MODE_BF16 ? 1 : 0])
+      return spn_tc_detector_head_fused(ctx, B, H, W, mode, d_mask, d_logits, d_prob, s);  // convPb + softmax fused
     if (!logits) logits = spn_tc_logits_scratch(ctx, B, H, W);
     if ((rc = spn_tc_detector_head(ctx, B, H, W, mode, logits, s))) return rc;
   }

@@ -105,6 +105,11 @@ int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_l
 int spn_tc_descriptor_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw, cudaStream_t s);
 void spn_tc_destroy(spn_ctx* ctx);
 const float* spn_tc_bias(spn_ctx* ctx, int layer);
+int spn_head_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float* h_bfold);
+int spn_launch_head_tc(spn_ctx* ctx, int mode, const void* in, int n_img, int Hc, int Wc, const uint8_t* d_mask, float* d_logits,
+                       float* d_prob, cudaStream_t s);
+int spn_tc_detector_head_fused(spn_ctx* ctx, int B, int H, int W, int mode, const uint8_t* d_mask, float* d_logits, float* d_prob,
+                               cudaStream_t s);
 void* spn_tc_encode_fn(spn_ctx* ctx);  // cuTensorMapEncodeTiled, or nullptr (error set)
 int spn_fold_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float* h_bfold);
 int spn_launch_conv_fold(spn_ctx* ctx, int layer, int mode, const void* in, void* out, int n_img, int H, int W, bool relu,

@@ -140,3 +140,47 @@ def test_forward_fast_other_sizes_vs_oracle(shape):
     e3 = rel_err(got["descriptor_output"]["desc_raw"].cpu().numpy(), want["descriptor_output"]["desc_raw"].numpy())
     print(f"{shape}: logits {e1:.2e} prob {e2:.2e} desc_raw {e3:.2e}")
     assert e1 < FAST and e2 < FAST and e3 < FAST, (e1, e2, e3)
+
+
+def test_fused_head_matches_unfused(monkeypatch):
+    """convPb + softmax + depth-to-space + mask in one kernel (head_tc.cu) vs conv_tc<1> + softmax_d2s_kernel:
+    same 16-bit operands and fp32 accumulation, so logits and heatmaps agree to fp32 rounding."""
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    sd = O.make_state_dict("magicpoint", seed=7, logit_gain=8.0)
+    c = copy.deepcopy(MP_MODEL)
+    c["precision"] = "f16"
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    ctx = m.native()
+    for (B, H, W) in [(3, 240, 320), (2, 40, 72), (1, 136, 8)]:
+        x = torch.from_numpy(np.stack([smooth_image(H, W, 30 + i) for i in range(B)])).cuda()
+        mask = (torch.rand((B, H, W), device="cuda") > 0.2).to(torch.uint8)
+        outs = {}
+        for tag, env in (("unfused", "1"), ("fused", "0")):
+            monkeypatch.setenv("SPN_TC_NOHEADFUSE", env)
+            ctx.encoder_forward(x, m.mode)
+            prob, logits = ctx.detector_head_forward(B, H, W, m.mode, mask=mask, want_logits=True)
+            ctx.encoder_forward(x, m.mode)
+            prob2, _ = ctx.detector_head_forward(B, H, W, m.mode, mask=None, want_logits=False)
+            outs[tag] = (prob.clone(), logits.clone(), prob2.clone())
+        for a, b in zip(outs["fused"], outs["unfused"]):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-5   # fast exp in the fused kernel: ~1e-6 relative
+
+
+@pytest.mark.parametrize("name,shape", [("backbone.block_3", (2, 64, 48, 40)), ("backbone.block_6", (1, 128, 60, 80))])
+def test_unfolded_conv_kernel_still_correct(sp_model, monkeypatch, name, shape):
+    """conv_tc_kernel<9> (nine shifted descriptors, N = 64) is the formulation used inside front_tc_kernel and the
+    SPN_TC_FOLD=0 fallback for the other 3x3 layers: keep it covered."""
+    m, sd = sp_model
+    ctx = m.native()
+    lid = LAYER_ID[name]
+    _n, cin, cout, k, relu, pool = O.layer_table(superpoint=True)[lid]
+    rng = np.random.RandomState(lid + 100)
+    x = torch.from_numpy(np.maximum(rng.randn(*shape), 0).astype(np.float32))
+    want = O.vgg_block(sd, name, x.half().float(), k, relu, pool).numpy()
+    monkeypatch.setenv("SPN_TC_FOLD", "0")
+    a = ctx.conv_layer(lid, x.cuda(), 1, relu=relu, pool=pool, cout=cout).cpu().numpy()
+    monkeypatch.setenv("SPN_TC_FOLD", "1")
+    b = ctx.conv_layer(lid, x.cuda(), 1, relu=relu, pool=pool, cout=cout).cpu().numpy()
+    assert rel_err(a, want) < FAST and rel_err(b, want) < FAST
+    assert rel_err(a, b) < 2e-3      # same operands, different summation order + one fp16 rounding
