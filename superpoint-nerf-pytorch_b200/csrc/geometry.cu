@@ -402,6 +402,7 @@ resize_crop_kernel(const T* __restrict__ src, int H0, int W0, int nh, int nw, in
 extern "C" int spn_resize_crop(spn_ctx* ctx, const void* d_src, int src_is_u8, int H0, int W0, int new_h, int new_w,
                                int crop_top, int crop_left, int H, int W, float divisor, float* d_out, spn_stream stream) {
   SPN_REQUIRE(ctx && d_src && d_out, "spn_resize_crop: null pointer");
+  SPN_CUDA(cudaSetDevice(ctx->device));
   SPN_REQUIRE(H0 > 0 && W0 > 0 && new_h > 0 && new_w > 0 && H > 0 && W > 0 && divisor != 0.f, "spn_resize_crop: bad shape");
   dim3 grid(spn_cdiv(W, 32), spn_cdiv(H, 8));
   if (src_is_u8)
@@ -417,6 +418,7 @@ extern "C" int spn_resize_crop(spn_ctx* ctx, const void* d_src, int src_is_u8, i
 extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H,
                               int W, int margin, float* d_warped, uint8_t* d_mask, spn_stream stream) {
   SPN_REQUIRE(ctx && d_images && d_mask, "spn_warp_batch: null pointer");
+  SPN_CUDA(cudaSetDevice(ctx->device));
   SPN_REQUIRE(n_images > 0 && n_h >= 0 && H > 0 && W > 0, "spn_warp_batch: bad shape");
   SPN_REQUIRE(n_h == 0 || d_hinv, "spn_warp_batch: d_hinv is null");
   // the reference's valid_border_margin == 0 path is shape-broken: unsupported
@@ -434,6 +436,7 @@ extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images,
 extern "C" int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float* d_h, int n_images, int n_h, int H,
                                 int W, int margin, int aggregation, float* d_out, spn_stream stream) {
   SPN_REQUIRE(ctx && d_probs && d_out, "spn_ha_aggregate: null pointer");
+  SPN_CUDA(cudaSetDevice(ctx->device));
   SPN_REQUIRE(n_images > 0 && n_images <= 65535 && n_h >= 0 && H > 0 && W > 0, "spn_ha_aggregate: bad shape");
   SPN_REQUIRE(n_h == 0 || d_h, "spn_ha_aggregate: d_h is null");
   SPN_REQUIRE(margin >= 1 && 2 * margin <= kMaxKs, "spn_ha_aggregate: valid_border_margin must be in [1,%d]", kMaxKs / 2);
@@ -453,6 +456,7 @@ extern "C" int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params
                                        uint64_t first_index, int count, int H, int W, float* d_h, float* d_hinv,
                                        spn_stream stream) {
   SPN_REQUIRE(ctx && params && d_h && d_hinv, "spn_sample_homographies: null pointer");
+  SPN_CUDA(cudaSetDevice(ctx->device));
   SPN_REQUIRE(count >= 0 && H > 0 && W > 0, "spn_sample_homographies: bad shape");
   SPN_REQUIRE(params->n_scales >= 1 && params->n_scales <= 31 && params->n_angles >= 1 && params->n_angles <= 63,
               "spn_sample_homographies: n_scales must be in [1,31], n_angles in [1,63]");
@@ -466,6 +470,7 @@ extern "C" int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params
 
 extern "C" int spn_invert3x3(spn_ctx* ctx, const float* d_in, int count, float* d_out, spn_stream stream) {
   SPN_REQUIRE(ctx && d_in && d_out && count >= 0, "spn_invert3x3: bad argument");
+  SPN_CUDA(cudaSetDevice(ctx->device));
   if (count == 0) return SPN_OK;
   invert3x3_kernel<<<spn_cdiv(count, 128), 128, 0, (cudaStream_t)stream>>>(d_in, count, d_out);
   SPN_CHECK_LAUNCH(ctx);
