@@ -25,6 +25,7 @@ constexpr int kRawH = kTileH + kMaxKs - 1, kRawW = kTileW + kMaxKs;  // 23 x 48
 struct ErodeK {
   int ks;              // structuring element is ks x ks
   int org;             // origin = ks/2
+  uint32_t rw_magic;   // ceil(2^32 / (kTileW + ks - 1)): row of a linearised halo index by one multiply-high
   uint32_t rows[kMaxKs];
 };
 
@@ -35,6 +36,7 @@ ErodeK make_ellipse(int margin) {
   const int ks = 2 * margin;
   e.ks = ks;
   e.org = ks / 2;
+  e.rw_magic = (uint32_t)(((1ull << 32) + (kTileW + ks - 1) - 1) / (kTileW + ks - 1));
   const int r = ks / 2, c = ks / 2;
   const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
   for (int i = 0; i < ks; ++i) {
@@ -54,34 +56,38 @@ ErodeK make_ellipse(int margin) {
 // The set of pixels p whose source coordinate M p satisfies a bound (sx >= a, sx <= b, ...) is a half-plane in p as
 // long as the homogeneous z stays positive, so for a rectangle of pixels it suffices to test its four corners:
 //   all four corners inside the source image (with a safety margin)  -> every pixel of the rectangle is valid,
-//   all four corners beyond the same source edge (with a margin)     -> every pixel is invalid and samples to zero.
+//   all four corners beyond the same source edge (with a margin)     -> every pixel is invalid and samples to zero,
+//   all four corners at least one pixel inside the source image      -> additionally every bilinear tap is in bounds
+//                                                                       ("deep": the aggregate's unchecked fast path).
 // Only tiles cut by the border of the warped quad need the per-pixel validity bits and the erosion.
-enum { kTileMixed = 0, kTileInside = 1, kTileOutside = 2 };
+enum { kTileMixed = 0, kTileInside = 1, kTileOutside = 2, kTileDeep = 3 };
 
-__device__ __forceinline__ int classify_tile(const float* m, const ErodeK& ek, int tx0, int ty0, int H, int W) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ int classify_tile(const float* m, const ErodeK& ek, int tx0, int ty0, int H, int W,
+                                             bool want_deep = false) {
   // halo rectangle clipped to the image (out-of-image neighbours never erode: geodesic border)
   const int xa = max(tx0 - ek.org, 0), xb = min(tx0 + kTileW - 1 + (ek.ks - ek.org - 1), W - 1);
   const int ya = max(ty0 - ek.org, 0), yb = min(ty0 + kTileH - 1 + (ek.ks - ek.org - 1), H - 1);
-  const float x = (lane & 1) ? (float)xb : (float)xa, y = (lane & 2) ? (float)yb : (float)ya;
-  const float nx = fmaf(m[0], x, fmaf(m[1], y, m[2]));
-  const float ny = fmaf(m[3], x, fmaf(m[4], y, m[5]));
-  const float z = fmaf(m[6], x, fmaf(m[7], y, m[8]));
-  const float sc = 1.0f / (z + 1e-8f);
-  const float sx = nx * sc, sy = ny * sc;
   const float mg = 1e-2f;
-  const bool zok = z > 1e-3f;
-  const bool in = zok && sx >= -0.5f + mg && sx <= (float)W - 0.5f - mg && sy >= -0.5f + mg && sy <= (float)H - 0.5f - mg;
-  const unsigned c4 = 0xFu;
-  const unsigned b_z = __ballot_sync(0xffffffffu, zok) & c4;
-  const unsigned b_in = __ballot_sync(0xffffffffu, in) & c4;
-  const unsigned b_l = __ballot_sync(0xffffffffu, sx < -1.0f - mg) & c4;
-  const unsigned b_r = __ballot_sync(0xffffffffu, sx > (float)W + mg) & c4;
-  const unsigned b_t = __ballot_sync(0xffffffffu, sy < -1.0f - mg) & c4;
-  const unsigned b_b = __ballot_sync(0xffffffffu, sy > (float)H + mg) & c4;
-  if (b_z != c4) return kTileMixed;
-  if (b_in == c4) return kTileInside;
-  if (b_l == c4 || b_r == c4 || b_t == c4 || b_b == c4) return kTileOutside;
+  bool zok = true, in = true, deep = true, l = true, r = true, t = true, b = true;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float x = (c & 1) ? (float)xb : (float)xa, y = (c & 2) ? (float)yb : (float)ya;
+    const float nx = fmaf(m[0], x, fmaf(m[1], y, m[2]));
+    const float ny = fmaf(m[3], x, fmaf(m[4], y, m[5]));
+    const float z = fmaf(m[6], x, fmaf(m[7], y, m[8]));
+    const float sc = 1.0f / (z + 1e-8f);
+    const float sx = nx * sc, sy = ny * sc;
+    zok = zok && z > 1e-3f;
+    in = in && sx >= -0.5f + mg && sx <= (float)W - 0.5f - mg && sy >= -0.5f + mg && sy <= (float)H - 0.5f - mg;
+    deep = deep && sx >= mg && sx <= (float)W - 1.0f - mg && sy >= mg && sy <= (float)H - 1.0f - mg;
+    l = l && sx < -1.0f - mg;
+    r = r && sx > (float)W + mg;
+    t = t && sy < -1.0f - mg;
+    b = b && sy > (float)H + mg;
+  }
+  if (!zok) return kTileMixed;
+  if (in) return (deep && want_deep) ? kTileDeep : kTileInside;
+  if (l || r || t || b) return kTileOutside;
   return kTileMixed;
 }
 
@@ -98,7 +104,7 @@ __device__ __forceinline__ void fill_raw_bits(uint32_t* bits, const float* m, co
     const int i = base + lane;
     int v = 0;
     if (i < n) {
-      const int ry = i / rw, rx = i - ry * rw;
+      const int ry = (int)__umulhi((unsigned)i, ek.rw_magic), rx = i - ry * rw;  // i < 2^11: exact
       const int y = ty0 + ry - ek.org, x = tx0 + rx - ek.org;
       v = 1;
       if (x >= 0 && x < W && y >= 0 && y < H) {
@@ -112,100 +118,201 @@ __device__ __forceinline__ void fill_raw_bits(uint32_t* bits, const float* m, co
   }
 }
 
-__device__ __forceinline__ int eroded_bits(const uint32_t* bits, const ErodeK& ek, int tx, int ty) {
-  const int rw = kTileW + ek.ks - 1;
+// `rows` = the structuring element's row masks in shared memory (a kernel parameter indexed by a loop counter would
+// be spilled to local memory).
+__device__ __forceinline__ int eroded_bits(const uint32_t* bits, const uint32_t* rows, int ks, int tx, int ty) {
+  const int rw = kTileW + ks - 1;
   int ok = 1;
-  for (int i = 0; i < ek.ks; ++i) {
-    const int o = (ty + i) * rw + tx;
+  int o = ty * rw + tx;
+  for (int i = 0; i < ks; ++i, o += rw) {
     const uint32_t lo = bits[o >> 5], hi = bits[(o >> 5) + 1];
     const uint32_t w = __funnelshift_r(lo, hi, o & 31);
-    const uint32_t rm = ek.rows[i];
+    const uint32_t rm = rows[i];
     ok &= ((w & rm) == rm);
   }
   return ok;
 }
 
+// One block per (row of tiles, slot).  The first threads classify the row's tiles (one thread per tile, four corner
+// projections each); the block then walks the tiles: uniform ones are a plain store, tiles cut by the warped quad's
+// border go through the validity bits + erosion (bit buffers double buffered: one barrier per mixed tile).
+constexpr int kMaxRowTiles = 256;
+
 __global__ void __launch_bounds__(256)
 warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hinv, int n_h, int H, int W,
                   int tiles_x, ErodeK ek, float* __restrict__ warped, uint8_t* __restrict__ mask) {
-  __shared__ uint32_t bits[kRawWords];
+  __shared__ uint32_t bits[2][kRawWords];
   __shared__ float m[9];
+  __shared__ uint32_t rows_s[kMaxKs];
+  __shared__ uint8_t cls_s[kMaxRowTiles];
   const int slot = blockIdx.y;
   const int img = slot / (n_h + 1), j = slot - img * (n_h + 1);
-  const int tx0 = (blockIdx.x % tiles_x) * kTileW, ty0 = (blockIdx.x / tiles_x) * kTileH;
+  const int ty0 = blockIdx.x * kTileH;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int x = tx0 + tx, y = ty0 + ty;
+  const int y = ty0 + ty;
   const float* src = images + (size_t)img * H * W;
-  const size_t o = ((size_t)slot * H + y) * W + x;
-  const bool in_img = x < W && y < H;
+  const size_t orow = ((size_t)slot * H + y) * W;
   if (j == 0) {  // identity forward (export.py:93): the image itself, no mask
-    if (in_img) {
-      if (warped) warped[o] = __ldg(&src[(size_t)y * W + x]);
-      mask[o] = 1;
-    }
+    if (y < H)
+      for (int x = tx; x < W; x += 32) {
+        if (warped) warped[orow + x] = __ldg(&src[(size_t)y * W + x]);
+        mask[orow + x] = 1;
+      }
     return;
   }
   if (threadIdx.x < 9) m[threadIdx.x] = __ldg(&hinv[((size_t)img * n_h + (j - 1)) * 9 + threadIdx.x]);
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + kMaxKs) rows_s[threadIdx.x - 32] = ek.rows[threadIdx.x - 32];
   __syncthreads();
-  const int cls = classify_tile(m, ek, tx0, ty0, H, W);  // identical in every warp of the block
-  if (cls == kTileOutside) {
+  for (int t = threadIdx.x; t < tiles_x; t += blockDim.x) cls_s[t] = (uint8_t)classify_tile(m, ek, t * kTileW, ty0, H, W);
+  __syncthreads();
+  int nmixed = 0;
+  for (int t = 0; t < tiles_x; ++t) {
+    const int cls = cls_s[t];  // block-uniform
+    const int tx0 = t * kTileW, x = tx0 + tx;
+    const bool in_img = x < W && y < H;
+    if (cls == kTileOutside) {
+      if (in_img) {
+        if (warped) warped[orow + x] = 0.f;
+        mask[orow + x] = 0;
+      }
+      continue;
+    }
+    int mk = 1;
+    if (cls == kTileMixed) {
+      uint32_t* bb = bits[nmixed & 1];
+      ++nmixed;
+      fill_raw_bits(bb, m, ek, tx0, ty0, H, W);
+      __syncthreads();
+      mk = eroded_bits(bb, rows_s, ek.ks, tx, ty);
+    }
     if (in_img) {
-      if (warped) warped[o] = 0.f;
-      mask[o] = 0;
+      if (warped) {  // null: mask only (the fused encoder warps on the fly)
+        float sx, sy;
+        apply_h(m, (float)x, (float)y, sx, sy);
+        warped[orow + x] = bilinear_zero(src, sx, sy, H, W);
+      }
+      mask[orow + x] = (uint8_t)mk;
     }
-    return;
-  }
-  int mk = 1;
-  if (cls == kTileMixed) {
-    fill_raw_bits(bits, m, ek, tx0, ty0, H, W);
-    __syncthreads();
-    mk = eroded_bits(bits, ek, tx, ty);
-  }
-  if (in_img) {
-    if (warped) {  // null: mask only (the fused encoder warps on the fly)
-      float sx, sy;
-      apply_h(m, (float)x, (float)y, sx, sy);
-      warped[o] = bilinear_zero(src, sx, sy, H, W);
-    }
-    mask[o] = (uint8_t)mk;
   }
 }
 
-__global__ void __launch_bounds__(256)
+struct DeepTaps {
+  float v00, v01, v10, v11, ax, ay;
+};
+
+// Issue the four loads of one bilinear sample whose taps are all inside the image (tile class "deep").
+__device__ __forceinline__ DeepTaps deep_taps(const float* __restrict__ pimg, const float4* __restrict__ hs4,
+                                              const float* __restrict__ hs, int j, int hw, int W, float fx, float fy) {
+  const float4 r0 = hs4[j * 3], r1 = hs4[j * 3 + 1];
+  const float m8 = hs[j * 12 + 8];
+  const float nx = fmaf(r0.x, fx, fmaf(r0.y, fy, r0.z));
+  const float ny = fmaf(r0.w, fx, fmaf(r1.x, fy, r1.y));
+  const float z = fmaf(r1.z, fx, fmaf(r1.w, fy, m8));
+  const float sc = rcp_normal(z + 1e-8f);
+  const float sx = nx * sc, sy = ny * sc;
+  const float flx = floorf(sx), fly = floorf(sy);
+  const float* p = pimg + ((j + 1) * hw + (int)fly * W + (int)flx);
+  DeepTaps t;
+  t.v00 = __ldg(p);
+  t.v01 = __ldg(p + 1);
+  t.v10 = __ldg(p + W);
+  t.v11 = __ldg(p + W + 1);
+  t.ax = sx - flx;
+  t.ay = sy - fly;
+  return t;
+}
+
+__device__ __forceinline__ float deep_value(const DeepTaps& t) {
+  const float top = fmaf(t.ax, t.v01 - t.v00, t.v00), bot = fmaf(t.ax, t.v11 - t.v10, t.v10);
+  return fmaf(t.ay, bot - top, top);
+}
+
+// One block per 32 x 8 output tile of one image.  The homographies are first classified for this tile; the "deep"
+// ones (most of them: whole tile valid, all taps in bounds) run as a barrier-free loop with two samples in flight per
+// thread; the tiles cut by a warped border go through the validity bits + erosion.
+__global__ void __launch_bounds__(256, 4)
 ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ hmat, int n_h, int H, int W,
                     int tiles_x, ErodeK ek, int agg_max, float* __restrict__ out) {
-  extern __shared__ float hs[];  // n_h * 9
+  extern __shared__ float4 hs4[];  // n_h homographies padded to 12 floats, then three byte arrays of n_h entries
   __shared__ uint32_t bits[2][kRawWords];
+  __shared__ uint32_t rows_s[kMaxKs];
+  __shared__ int n_list[2];
+  float* hs = reinterpret_cast<float*>(hs4);
+  uint8_t* cls_s = reinterpret_cast<uint8_t*>(hs + n_h * 12);
+  uint8_t* deep_s = cls_s + ((n_h + 15) & ~15);
+  uint8_t* rest_s = deep_s + ((n_h + 15) & ~15);
   const int img = blockIdx.y;
   const int tx0 = (blockIdx.x % tiles_x) * kTileW, ty0 = (blockIdx.x / tiles_x) * kTileH;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int x = tx0 + tx, y = ty0 + ty;
+  const float fx = (float)x, fy = (float)y;
   const bool in_img = x < W && y < H;
-  for (int i = threadIdx.x; i < n_h * 9; i += blockDim.x) hs[i] = __ldg(&hmat[(size_t)img * n_h * 9 + i]);
+  for (int i = threadIdx.x; i < n_h * 9; i += blockDim.x) hs[(i / 9) * 12 + i % 9] = __ldg(&hmat[(size_t)img * n_h * 9 + i]);
+  if (threadIdx.x < kMaxKs) rows_s[threadIdx.x] = ek.rows[threadIdx.x];
   const float* pimg = probs + (size_t)img * (n_h + 1) * H * W;
+  const int hw = H * W;
   float acc = 0.f, cnt = 1.f, mx = 0.f;
   if (in_img) {
-    acc = __ldg(&pimg[(size_t)y * W + x]);
+    acc = __ldg(&pimg[y * W + x]);
     mx = acc;
   }
   __syncthreads();
+  for (int j = threadIdx.x; j < n_h; j += blockDim.x)
+    cls_s[j] = (uint8_t)classify_tile(hs + j * 12, ek, tx0, ty0, H, W, true);
+  __syncthreads();
+  if (threadIdx.x < 32) {  // ordered compaction into the two work lists (outside tiles contribute nothing: dropped)
+    int nd = 0, nr = 0;
+    for (int base = 0; base < n_h; base += 32) {
+      const int j = base + threadIdx.x;
+      const int c = j < n_h ? cls_s[j] : kTileOutside;
+      const unsigned md = __ballot_sync(0xffffffffu, c == kTileDeep);
+      const unsigned mr = __ballot_sync(0xffffffffu, c == kTileMixed || c == kTileInside);
+      const unsigned lt = (1u << threadIdx.x) - 1u;
+      if (c == kTileDeep) deep_s[nd + __popc(md & lt)] = (uint8_t)j;
+      if (c == kTileMixed || c == kTileInside) rest_s[nr + __popc(mr & lt)] = (uint8_t)j;
+      nd += __popc(md);
+      nr += __popc(mr);
+    }
+    if (threadIdx.x == 0) {
+      n_list[0] = nd;
+      n_list[1] = nr;
+    }
+  }
+  __syncthreads();
+  const int n_deep = n_list[0], n_rest = n_list[1];
+  if (in_img) {
+    int k = 0;
+    for (; k + 1 < n_deep; k += 2) {
+      const DeepTaps a = deep_taps(pimg, hs4, hs, deep_s[k], hw, W, fx, fy);
+      const DeepTaps b = deep_taps(pimg, hs4, hs, deep_s[k + 1], hw, W, fx, fy);
+      const float va = deep_value(a), vb = deep_value(b);
+      acc += va;
+      acc += vb;
+      mx = fmaxf(mx, fmaxf(va, vb));
+    }
+    if (k < n_deep) {
+      const float va = deep_value(deep_taps(pimg, hs4, hs, deep_s[k], hw, W, fx, fy));
+      acc += va;
+      mx = fmaxf(mx, va);
+    }
+    cnt += (float)n_deep;
+  }
   int nmixed = 0;
-  for (int j = 0; j < n_h; ++j) {
-    const float* m = hs + j * 9;
-    const int cls = classify_tile(m, ek, tx0, ty0, H, W);  // block-uniform
-    if (cls == kTileOutside) continue;                      // count == 0 on the whole tile: contributes nothing
+  for (int k = 0; k < n_rest; ++k) {
+    const int j = rest_s[k];
+    const float* m = hs + j * 12;
     int c = 1;
-    if (cls == kTileMixed) {
-      uint32_t* bb = bits[nmixed & 1];  // double buffered: one barrier per mixed homography
+    if (cls_s[j] == kTileMixed) {        // block-uniform
+      uint32_t* bb = bits[nmixed & 1];   // double buffered: one barrier per mixed homography
       ++nmixed;
       fill_raw_bits(bb, m, ek, tx0, ty0, H, W);
       __syncthreads();
-      c = eroded_bits(bb, ek, tx, ty);
+      c = eroded_bits(bb, rows_s, ek.ks, tx, ty);
     }
     if (in_img && c) {
       float sx, sy;
-      apply_h(m, (float)x, (float)y, sx, sy);
-      const float v = bilinear_zero(pimg + (size_t)(j + 1) * H * W, sx, sy, H, W);
+      apply_h(m, fx, fy, sx, sy);
+      const float v = bilinear_zero(pimg + (j + 1) * hw, sx, sy, H, W);
       acc += v;
       cnt += 1.f;
       mx = fmaxf(mx, v);
@@ -426,7 +533,8 @@ extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images,
   SPN_REQUIRE((size_t)n_images * (n_h + 1) <= 65535, "spn_warp_batch: too many slots per launch");
   const ErodeK ek = make_ellipse(margin);
   const int tiles_x = spn_cdiv(W, kTileW), tiles_y = spn_cdiv(H, kTileH);
-  dim3 grid(tiles_x * tiles_y, n_images * (n_h + 1));
+  SPN_REQUIRE(tiles_x <= kMaxRowTiles, "spn_warp_batch: W must be <= %d", kMaxRowTiles * kTileW);
+  dim3 grid(tiles_y, n_images * (n_h + 1));
   SpnProfScope prof(ctx, SPN_PROF_WARP, (cudaStream_t)stream);
   warp_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_images, d_hinv, n_h, H, W, tiles_x, ek, d_warped, d_mask);
   SPN_CHECK_LAUNCH(ctx);
@@ -441,12 +549,13 @@ extern "C" int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float*
   SPN_REQUIRE(n_h == 0 || d_h, "spn_ha_aggregate: d_h is null");
   SPN_REQUIRE(margin >= 1 && 2 * margin <= kMaxKs, "spn_ha_aggregate: valid_border_margin must be in [1,%d]", kMaxKs / 2);
   SPN_REQUIRE(aggregation == 0 || aggregation == 1, "spn_ha_aggregate: aggregation must be 0 (sum) or 1 (max)");
-  SPN_REQUIRE(n_h * 9 * sizeof(float) <= 40 * 1024, "spn_ha_aggregate: too many homographies per image");
+  SPN_REQUIRE(n_h <= 255, "spn_ha_aggregate: at most 255 homographies per image");
+  SPN_REQUIRE((size_t)(n_h + 1) * H * W < (1u << 30), "spn_ha_aggregate: (n_h + 1) * H * W must be below 2^30");
   const ErodeK ek = make_ellipse(margin);
   const int tiles_x = spn_cdiv(W, kTileW), tiles_y = spn_cdiv(H, kTileH);
   dim3 grid(tiles_x * tiles_y, n_images);
   SpnProfScope prof(ctx, SPN_PROF_AGGREGATE, (cudaStream_t)stream);
-  ha_aggregate_kernel<<<grid, 256, n_h * 9 * sizeof(float), (cudaStream_t)stream>>>(d_probs, d_h, n_h, H, W, tiles_x, ek,
+  ha_aggregate_kernel<<<grid, 256, n_h * 12 * sizeof(float) + 3 * ((n_h + 15) & ~15), (cudaStream_t)stream>>>(d_probs, d_h, n_h, H, W, tiles_x, ek,
                                                                                      aggregation, d_out);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;

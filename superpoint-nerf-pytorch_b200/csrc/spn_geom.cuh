@@ -5,12 +5,22 @@
 
 namespace spngeom {
 
+// Correctly rounded 1/z for z well inside the normal range (2^-100 < |z| < 2^100): the MUFU.RCP + one Newton step the
+// compiler emits for 1.0f / z, without its denormal/overflow guard and the branch that comes with it.
+__device__ __forceinline__ float rcp_normal(float z) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(z));
+  const float e = fmaf(-z, r, 1.0f);
+  return fmaf(r, e, r);
+}
+
 // src = M p  (p = (x, y, 1)) with kornia's homogeneous divide: scale = |z| > 1e-8 ? 1/(z + 1e-8) : 1
 __device__ __forceinline__ void apply_h(const float* __restrict__ m, float x, float y, float& sx, float& sy) {
   const float nx = fmaf(m[0], x, fmaf(m[1], y, m[2]));
   const float ny = fmaf(m[3], x, fmaf(m[4], y, m[5]));
   const float z = fmaf(m[6], x, fmaf(m[7], y, m[8]));
-  const float sc = fabsf(z) > 1e-8f ? 1.0f / (z + 1e-8f) : 1.0f;
+  // |z| > 1e-8 puts |z + 1e-8| in [~1e-15, |z| + 1e-8]: normal range for any finite homography
+  const float sc = fabsf(z) > 1e-8f ? rcp_normal(z + 1e-8f) : 1.0f;
   sx = nx * sc;
   sy = ny * sc;
 }
@@ -36,6 +46,17 @@ __device__ __forceinline__ float bilinear_zero(const float* __restrict__ img, fl
   if (yin1 && xin0) v = fmaf(__ldg(&img[(size_t)(y0 + 1) * W + x0]), wx0 * wy1, v);
   if (yin1 && xin1) v = fmaf(__ldg(&img[(size_t)(y0 + 1) * W + x0 + 1]), wx1 * wy1, v);
   return v;
+}
+
+// Bilinear sample whose four taps are known to be inside the image (0 <= floor(sx), floor(sx) + 1 <= W - 1, same in y):
+// no bounds tests, interpolation in lerp form.  `plane` is a 32-bit element offset into `img`.
+__device__ __forceinline__ float bilinear_inside(const float* __restrict__ img, int plane, float sx, float sy, int W) {
+  const float fx = floorf(sx), fy = floorf(sy);
+  const float ax = sx - fx, ay = sy - fy;
+  const float* p = img + (plane + (int)fy * W + (int)fx);
+  const float v00 = __ldg(p), v01 = __ldg(p + 1), v10 = __ldg(p + W), v11 = __ldg(p + W + 1);
+  const float top = fmaf(ax, v01 - v00, v00), bot = fmaf(ax, v11 - v10, v10);
+  return fmaf(ay, bot - top, top);
 }
 
 // Branch-free variant for latency-critical producers: the four taps are always loaded from clamped addresses and a
