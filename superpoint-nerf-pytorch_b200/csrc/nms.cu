@@ -192,6 +192,154 @@ nms_rounds_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ stat
   }
 }
 
+// Same fixed point for footprints of radius RAD <= 3 (box sizes up to 4, the reference's default), with the tile's
+// state held as two bit planes in shared memory - KEPT and GONE (suppressed or never a candidate), one 64-bit word
+// per halo row - so that every step is a fixed, branch-free sequence per warp:
+//   * warp w owns tile row w; a pixel's (2 RAD + 1)^2 neighbourhood is one funnel shift per row word, packed at
+//     8 bits per row (bit (dy + RAD) * 8 + (dx + RAD)), the layout of its `blockers` mask and of the footprint mask;
+//   * blockers = footprint & undecided-candidate neighbourhood & "outranks me" (one compare per tap, offsets known
+//     at compile time), collected once per visit;
+//   * suppressed iff (kept_nbhd & blockers) != 0, else blockers &= ~gone_nbhd and kept iff none remain;
+//   * newly decided pixels are published with two ballots per warp (a single writer per row word).
+// Tiles that still hold undecided pixels are appended to a compact list for the next round, so every round's work is
+// spread evenly over the grid; the iteration ends when that list is empty.
+template <int RAD>
+__global__ void __launch_bounds__(kThreads, 2)
+nms_rounds_bits_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ status_all, uint32_t foot_lo,
+                       uint32_t foot_hi, int B, int H, int W, float min_prob, int tiles_x, int tiles_y,
+                       unsigned* __restrict__ pend, int* __restrict__ lists) {
+  cg::grid_group grid = cg::this_grid();
+  constexpr int R = 2 * RAD + 1, HT = 32 + 2 * RAD, HP = HT + 1;
+  constexpr uint32_t rowbits = (1u << R) - 1u;
+  __shared__ uint64_t kept[HT], gone[HT];
+  __shared__ float sc[HT * HP];
+  __shared__ uint8_t st[HT * HP];
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const size_t P = (size_t)H * W;
+  const int n_tiles = B * tiles_x * tiles_y;
+
+  for (size_t i = (size_t)blockIdx.x * kThreads + tid; i < (size_t)B * P; i += (size_t)gridDim.x * kThreads)
+    status_all[i] = (__ldg(&prob_all[i]) >= min_prob) ? 1 : 0;
+  for (int i = blockIdx.x * kThreads + tid; i < n_tiles; i += gridDim.x * kThreads) lists[i] = i;
+  if (blockIdx.x == 0 && tid < 8) pend[tid] = tid == 0 ? (unsigned)n_tiles : 0u;
+  grid.sync();
+
+  // pend[k % 3] = length of the tile list consumed in round k; lists[(k & 1) * n_tiles ...] holds it
+  for (int round = 0;; ++round) {
+    const int n_cur = (int)__ldcg(&pend[round % 3]);
+    const int* cur = lists + (round & 1) * n_tiles;
+    int* nxt = lists + ((round + 1) & 1) * n_tiles;
+    unsigned* n_nxt = &pend[(round + 1) % 3];
+    if (blockIdx.x == 0 && tid == 0) pend[(round + 2) % 3] = 0;  // consumed in round - 1, appended to in round + 1
+    for (int idx = blockIdx.x; idx < n_cur; idx += gridDim.x) {
+      const int tile = __ldcg(&cur[idx]);
+      const int b = tile / (tiles_x * tiles_y), rem = tile - b * (tiles_x * tiles_y);
+      const int y0 = (rem / tiles_x) * 32 - RAD, x0 = (rem % tiles_x) * 32 - RAD;
+      const float* prob = prob_all + (size_t)b * P;
+      uint8_t* status = status_all + (size_t)b * P;
+      bool any_undecided = false;
+      for (int i = tid; i < HT * HT; i += kThreads) {
+        const int hy = i / HT, hx = i - hy * HT;
+        const int y = y0 + hy, x = x0 + hx;
+        uint8_t v = 0;
+        float s = 0.f;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+          v = __ldcg(&status[(size_t)y * W + x]);
+          if (v == 1) s = __ldg(&prob[(size_t)y * W + x]);
+          any_undecided |= (v == 1) && hy >= RAD && hy < HT - RAD && hx >= RAD && hx < HT - RAD;
+        }
+        st[hy * HP + hx] = v;
+        sc[hy * HP + hx] = s;
+      }
+      if (!__syncthreads_or(any_undecided)) continue;  // nothing left to decide here (also orders the smem fill)
+      // bit planes of the tile + halo
+      for (int hy = ty; hy < HT; hy += 32) {
+        const bool has1 = tx + 32 < HT;
+        const uint8_t v0 = st[hy * HP + tx], v1 = has1 ? st[hy * HP + tx + 32] : (uint8_t)0;
+        const unsigned k0 = __ballot_sync(0xffffffffu, v0 == 2), k1 = __ballot_sync(0xffffffffu, has1 && v1 == 2);
+        const unsigned g0 = __ballot_sync(0xffffffffu, v0 == 0), g1 = __ballot_sync(0xffffffffu, !has1 || v1 == 0);
+        if (tx == 0) {
+          kept[hy] = (uint64_t)k0 | ((uint64_t)k1 << 32);
+          gone[hy] = (uint64_t)g0 | ((uint64_t)g1 << 32);
+        }
+      }
+      const int cy = ty + RAD, cx = tx + RAD;
+      const int gy = y0 + cy, gx = x0 + cx;
+      const int me = cy * HP + cx;
+      int stv = st[me];
+      bool mine = stv == 1;
+      __syncthreads();  // planes complete
+      uint32_t bl = 0, bh = 0;  // undecided neighbours that outrank this pixel and overlap it ("blockers")
+      bool first = true;
+      for (int it = 0;; ++it) {
+        int res_new = 1;  // 0 / 2: decided in this step
+        if (__any_sync(0xffffffffu, mine)) {
+          uint32_t knl = 0, knh = 0, gnl = 0, gnh = 0;
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            const uint2 kw = *reinterpret_cast<const uint2*>(&kept[ty + i]);
+            const uint2 gw = *reinterpret_cast<const uint2*>(&gone[ty + i]);
+            const uint32_t kb = __funnelshift_r(kw.x, kw.y, tx) & rowbits;
+            const uint32_t gb = __funnelshift_r(gw.x, gw.y, tx) & rowbits;
+            if (i < 4) {
+              knl |= kb << (8 * i);
+              gnl |= gb << (8 * i);
+            } else {
+              knh |= kb << (8 * (i - 4));
+              gnh |= gb << (8 * (i - 4));
+            }
+          }
+          if (first) {  // warp-uniform: collect the blockers
+            const float sp = sc[me];
+            uint32_t ol = 0, oh = 0;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+#pragma unroll
+              for (int j = 0; j < R; ++j) {
+                if (i == RAD && j == RAD) continue;
+                const float sq = sc[me + (i - RAD) * HP + (j - RAD)];
+                const bool earlier = (i < RAD) || (i == RAD && j < RAD);  // row-major index tie break
+                const bool o = earlier ? (sq >= sp) : (sq > sp);
+                if (i < 4) ol |= (uint32_t)o << (8 * i + j); else oh |= (uint32_t)o << (8 * (i - 4) + j);
+              }
+            }
+            bl = ol & ~(knl | gnl) & foot_lo;
+            bh = oh & ~(knh | gnh) & foot_hi;
+          }
+          if (mine) {
+            if (((knl & foot_lo) | (knh & foot_hi)) != 0) {
+              res_new = 0;
+            } else {
+              bl &= ~gnl;
+              bh &= ~gnh;
+              if ((bl | bh) == 0) res_new = 2;
+            }
+            if (res_new != 1) { mine = false; stv = res_new; }
+          }
+        }
+        first = false;
+        const unsigned bk = __ballot_sync(0xffffffffu, res_new == 2), bg = __ballot_sync(0xffffffffu, res_new == 0);
+        if (tx == 0 && (bk | bg)) {
+          kept[cy] |= (uint64_t)bk << RAD;
+          gone[cy] |= (uint64_t)bg << RAD;
+        }
+        if (!__syncthreads_or((bk | bg) != 0)) break;
+        if (tid == 0) atomicAdd(&pend[4], 1u);  // statistics: local iterations
+      }
+      if (tid == 0) atomicAdd(&pend[5], 1u);    // statistics: tile visits with undecided pixels
+      bool still = false;
+      if (gy < H && gx < W) {
+        status[(size_t)gy * W + gx] = (uint8_t)stv;
+        still = stv == 1;
+      }
+      if (__syncthreads_or(still) && tid == 0) nxt[atomicAdd(n_nxt, 1u)] = tile;  // barrier: smem is reused next
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && tid == 0) pend[3] = (unsigned)round + 1;  // statistics: global rounds
+    if (__ldcg(n_nxt) == 0) break;
+  }
+}
+
 // Phase 2 (one CTA per image): optional top-k, scattered / thresholded maps, row-major keypoint list.
 __global__ void __launch_bounds__(kThreads)
 nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ status_all, int H, int W, int top_k,
@@ -347,23 +495,41 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
   cudaStream_t s = (cudaStream_t)stream;
   SPN_CUDA(cudaSetDevice(ctx->device));
   const size_t status_bytes = ((size_t)B * H * W + 255) & ~(size_t)255;
-  int rc = spn_ensure_aux(ctx, status_bytes + 256, s);
+  int tiles_x = spn_cdiv(W, 32), tiles_y = spn_cdiv(H, 32);
+  const long long n_tiles = (long long)B * tiles_x * tiles_y;
+  SPN_REQUIRE(n_tiles < (1ll << 28), "spn_box_nms_topk: batch too large");
+  int rc = spn_ensure_aux(ctx, status_bytes + 256 + 2 * (size_t)n_tiles * sizeof(int), s);
   if (rc) return rc;
   uint8_t* status = (uint8_t*)ctx->aux;
   unsigned* pend = (unsigned*)(ctx->aux + status_bytes);
+  int* lists = (int*)(ctx->aux + status_bytes + 256);
+  const bool bits_path = foot.r >= 1 && foot.r <= 3;  // box sizes up to 4: bit-plane kernel
+  uint32_t foot_lo = 0, foot_hi = 0;
+  if (bits_path)
+    for (int k = 0; k < foot.n; ++k) {
+      const int bit = (foot.dy[k] + foot.r) * 8 + foot.dx[k] + foot.r;
+      if (bit < 32) foot_lo |= 1u << bit; else foot_hi |= 1u << (bit - 32);
+    }
   const int HT = 32 + 2 * foot.r;
-  const size_t smem = (size_t)HT * (HT + 1) * 5 + 16;
+  const size_t smem = bits_path ? 0 : (size_t)HT * (HT + 1) * 5 + 16;
+  const void* kernel = foot.r == 1 ? (const void*)nms_rounds_bits_kernel<1>
+                     : foot.r == 2 ? (const void*)nms_rounds_bits_kernel<2>
+                     : foot.r == 3 ? (const void*)nms_rounds_bits_kernel<3> : (const void*)nms_rounds_kernel;
   int per_sm = 0;
-  SPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_rounds_kernel, kThreads, smem));
+  SPN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
   SPN_REQUIRE(per_sm >= 1, "spn_box_nms_topk: cooperative kernel does not fit on an SM");
-  int tiles_x = spn_cdiv(W, 32), tiles_y = spn_cdiv(H, 32);
-  const long long n_tiles = (long long)B * tiles_x * tiles_y;
   int grid = per_sm * ctx->sm_count;
   if (n_tiles < grid) grid = (int)n_tiles;
   SpnProfScope prof(ctx, SPN_PROF_NMS, s);
-  void* args[] = {(void*)&d_prob, (void*)&status, (void*)&foot, (void*)&B, (void*)&H, (void*)&W, (void*)&min_prob,
-                  (void*)&tiles_x, (void*)&tiles_y, (void*)&pend};
-  SPN_CUDA(cudaLaunchCooperativeKernel((void*)nms_rounds_kernel, dim3(grid), dim3(kThreads), args, smem, s));
+  if (bits_path) {
+    void* args[] = {(void*)&d_prob, (void*)&status, (void*)&foot_lo, (void*)&foot_hi, (void*)&B, (void*)&H, (void*)&W,
+                    (void*)&min_prob, (void*)&tiles_x, (void*)&tiles_y, (void*)&pend, (void*)&lists};
+    SPN_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), args, smem, s));
+  } else {
+    void* args[] = {(void*)&d_prob, (void*)&status, (void*)&foot, (void*)&B, (void*)&H, (void*)&W, (void*)&min_prob,
+                    (void*)&tiles_x, (void*)&tiles_y, (void*)&pend};
+    SPN_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), args, smem, s));
+  }
   ctx->launches++;
   nms_finalize_kernel<<<B, kThreads, 0, s>>>(d_prob, status, H, W, top_k, det_thresh, d_nms, d_pred, d_kp, d_kp_count, max_kp);
   SPN_CHECK_LAUNCH(ctx);
