@@ -55,6 +55,7 @@ conv_fold_kernel(const __grid_constant__ CUtensorMap tmap, const FoldParams p) {
   __shared__ __align__(8) uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_w, bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
 
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wbytes = p.cin_blocks * 12 * kBlkBytes + kBlkBytes;
   uint8_t* wsm = smem;
@@ -94,6 +95,7 @@ conv_fold_kernel(const __grid_constant__ CUtensorMap tmap, const FoldParams p) {
       const uint8_t* wsrc = (const uint8_t*)p.wimg + (size_t)slice * wbytes;
       for (int o = 0; o < wbytes; o += kBlkBytes) bulk_load(wsm + o, wsrc + o, kBlkBytes, &bar_w);
     }
+    griddep_wait();  // the activations come from the previous kernel; every store of this CTA follows these loads
     int stage = 0;
     uint32_t phase = 0;
     for (int t = cta_in_slice; t < n_tiles; t += ctas_per_slice) {
@@ -324,7 +326,7 @@ int spn_launch_conv_fold(spn_ctx* ctx, int layer, int mode, const void* in, void
   grid = grid / p.cout_slices * p.cout_slices;
   if (grid < p.cout_slices) grid = p.cout_slices;
   SpnProfScope prof(ctx, layer, s);
-  conv_fold_kernel<<<grid, kThreads, dyn, s>>>(tmap, p);
+  SPN_CUDA(spn_launch_pdl(conv_fold_kernel, dim3(grid), dim3(kThreads), dyn, s, tmap, p));
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
   uint8_t* ones = a1s + kNA1 * kA1Bytes;                // 4096          (at 102400)
   uint8_t* slab0 = ones + kOnesBytes;                   // kStages x 23552  (at 106496 = 104 x 1024)
 
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int n_tiles = p.n_slots * tiles_per_img;
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
   } else if (warp >= 10) {
     // ===================== P: warped patch + im2col operand of block_1 =====================
     const int pt = threadIdx.x - 320;  // 0..255
+    griddep_wait();  // the output buffer may still be read by the previous chunk's kernels; every store follows P's data
     float hm[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     int hm_slot = -1;
     int i = 0;
@@ -353,7 +355,7 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
   const long long tiles = (long long)n_slots * p.tiles_x * p.tiles_y;
   const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
   SpnProfScope prof(ctx, SPN_L_BLOCK2, s);
-  front_tc_kernel<<<grid, kThreads, dyn, s>>>(p);
+  SPN_CUDA(spn_launch_pdl(front_tc_kernel, dim3(grid), dim3(kThreads), dyn, s, p));
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }

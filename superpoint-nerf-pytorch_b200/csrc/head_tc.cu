@@ -47,6 +47,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadParams p) {
   __shared__ __align__(8) uint64_t bar_full[kStages], bar_empty[kStages], bar_w, bar_tfull[2], bar_tempty[2];
   __shared__ uint32_t tmem_base_s;
 
+  griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* wsm = smem;
   uint8_t* ones = smem + ((kWBytes + 1023) & ~1023);
@@ -80,6 +81,7 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadParams p) {
       mbar_expect_tx(&bar_w, (uint32_t)kWBytes);
       for (int o = 0; o < kWBytes; o += kBlk) bulk_load(wsm + o, (const uint8_t*)p.wimg + o, kBlk, &bar_w);
     }
+    griddep_wait();  // convPa's output comes from the previous kernel; every store of this CTA follows these loads
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -272,7 +274,7 @@ int spn_launch_head_tc(spn_ctx* ctx, int mode, const void* in, int n_img, int Hc
   const long long tiles = (long long)n_img * p.tiles_x * p.tiles_y;
   const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
   SpnProfScope prof(ctx, SPN_L_CONVPB, s);
-  head_tc_kernel<<<grid, kThreads, dyn, s>>>(tmap, p);
+  SPN_CUDA(spn_launch_pdl(head_tc_kernel, dim3(grid), dim3(kThreads), dyn, s, tmap, p));
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }

@@ -89,6 +89,26 @@ struct SpnProfScope {
   }
 };
 
+// Launch with programmatic stream serialization: the kernel may begin (prologue: barriers, TMEM, weights) while the
+// previous kernel of the stream drains; it must execute griddepcontrol.wait before touching anything that kernel
+// wrote or read.  SPN_NO_PDL=1 falls back to a plain launch.
+template <typename... KArgs, typename... Args>
+inline cudaError_t spn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t dyn, cudaStream_t s, Args&&... args) {
+  static const bool off = getenv("SPN_NO_PDL") && atoi(getenv("SPN_NO_PDL")) != 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 int spn_ensure_ws(spn_ctx* ctx, size_t bytes, cudaStream_t s);
 int spn_ensure_aux(spn_ctx* ctx, size_t bytes, cudaStream_t s);
 
