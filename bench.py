@@ -314,7 +314,10 @@ def run_native(args):
 
     imgs_rank = ips * args.steps
     kernels = [tensor_entry(n) for n in LAYER_FLOPS]
-    kernels += [hbm_entry("warp_batch", imgs_rank * (NUM_H - 1) * 4 * H * W * 2),                 # 614.4 KB / homography
+    # fast modes: the image warp is fused into front_tc_kernel, warp_batch only writes the 1-byte validity masks;
+    # strict fp32 mode: it also reads the image and writes the warped copy (614.4 KB / homography)
+    warp_bytes = NUM_H * H * W if args.precision != "fp32" else (NUM_H - 1) * 4 * H * W * 2 + NUM_H * H * W
+    kernels += [hbm_entry("warp_batch", imgs_rank * warp_bytes),
                 hbm_entry("ha_aggregate", imgs_rank * (NUM_H * 4 * H * W + 4 * H * W)),              # 30.7 MB read + 307 KB written / image
                 hbm_entry("softmax_d2s", imgs_rank * NUM_H * (65 * (H // 8) * (W // 8) * 4 + 4 * H * W)),
                 hbm_entry("box_nms", imgs_rank * 4 * H * W * 2)]

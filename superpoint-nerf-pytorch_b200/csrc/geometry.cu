@@ -282,15 +282,19 @@ ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ h
   const int n_deep = n_list[0], n_rest = n_list[1];
   if (in_img) {
     int k = 0;
-    for (; k + 1 < n_deep; k += 2) {
+    for (; k + 3 < n_deep; k += 4) {  // four samples (16 loads) in flight per thread
       const DeepTaps a = deep_taps(pimg, hs4, hs, deep_s[k], hw, W, fx, fy);
       const DeepTaps b = deep_taps(pimg, hs4, hs, deep_s[k + 1], hw, W, fx, fy);
-      const float va = deep_value(a), vb = deep_value(b);
+      const DeepTaps c = deep_taps(pimg, hs4, hs, deep_s[k + 2], hw, W, fx, fy);
+      const DeepTaps d = deep_taps(pimg, hs4, hs, deep_s[k + 3], hw, W, fx, fy);
+      const float va = deep_value(a), vb = deep_value(b), vc = deep_value(c), vd = deep_value(d);
       acc += va;
       acc += vb;
-      mx = fmaxf(mx, fmaxf(va, vb));
+      acc += vc;
+      acc += vd;
+      mx = fmaxf(fmaxf(mx, fmaxf(va, vb)), fmaxf(vc, vd));
     }
-    if (k < n_deep) {
+    for (; k < n_deep; ++k) {
       const float va = deep_value(deep_taps(pimg, hs4, hs, deep_s[k], hw, W, fx, fy));
       acc += va;
       mx = fmaxf(mx, va);

@@ -184,3 +184,26 @@ def test_unfolded_conv_kernel_still_correct(sp_model, monkeypatch, name, shape):
     b = ctx.conv_layer(lid, x.cuda(), 1, relu=relu, pool=pool, cout=cout).cpu().numpy()
     assert rel_err(a, want) < FAST and rel_err(b, want) < FAST
     assert rel_err(a, b) < 2e-3      # same operands, different summation order + one fp16 rounding
+
+
+def test_fast_path_is_deterministic_across_chunkings():
+    """The tensor-core kernels are chained with programmatic dependent launch and reuse two activation buffers from
+    chunk to chunk: the result must not depend on how the homography slots are chunked, nor vary from run to run
+    (a missed dependency would show up as a racy difference)."""
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import HomographyAdaptation
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    sd = O.make_state_dict("magicpoint", seed=5, logit_gain=8.0)
+    c = copy.deepcopy(MP_MODEL)
+    c["precision"] = "f16"
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    imgs = torch.from_numpy(np.stack([smooth_image(120, 160, 10 + i) for i in range(3)])).cuda().unsqueeze(1)
+    outs = []
+    for max_forwards in (7, 7, 16, 400):
+        ha = dict(copy.deepcopy(HA_CFG), num=12, sampler="device", seed=99, max_forwards=max_forwards)
+        eng = HomographyAdaptation({"homography_adaptation": ha, "model": c}, m, "cuda")
+        for _ in range(3):
+            heat, _ = eng.heatmaps(imgs, first_index=0)
+            outs.append(heat.clone())
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
