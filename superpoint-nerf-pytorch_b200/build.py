@@ -7,6 +7,7 @@ No torch involvement: plain `nvcc -shared`.  The .so is git-ignored but travels 
 from __future__ import annotations
 
 import subprocess
+import os
 import sys
 from pathlib import Path
 
@@ -36,6 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in SOURCES:
         obj = bdir / (src + ".o")
         cmd = ["nvcc", *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"], "-c", str(CSRC / src), "-o", str(obj)]
+        if os.environ.get("SPN_FRONT_DBG_BUILD"):   # extra front_tc_kernel instantiations for tools/front_probe.py
+            cmd.insert(1, "-DSPN_FRONT_DBG_BUILD")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

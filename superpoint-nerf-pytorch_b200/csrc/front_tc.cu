@@ -66,6 +66,8 @@ __device__ __forceinline__ uint16_t to16(float v, int bf) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
+// DBG != 0 instantiations switch parts of the roles off (bottleneck experiments, tools/front_probe.py; wrong results).
+template <int DBG>
 __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_w, bar_a1_full[kNA1], bar_a1_empty[kNA1], bar_d1_full[kNA1], bar_d1_empty[kNA1],
@@ -113,16 +115,21 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
   const uint32_t fmt = p.is_bf16 ? 1u : 0u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
-  if (warp == 0) {
-    // ===================== weight loader =====================
-    if (elect_one()) {
-      mbar_expect_tx(&bar_w, (uint32_t)(kW2Bytes + kW1Bytes));
-      for (int o = 0; o + 8192 <= kW2Bytes; o += 8192) bulk_load(w2s + o, (const uint8_t*)p.w2img + o, 8192, &bar_w);
-      bulk_load(w2s + 9 * 8192, (const uint8_t*)p.w2img + 9 * 8192, 2048, &bar_w);
-      bulk_load(w1s, p.w1img, kW1Bytes, &bar_w);
+  if (warp <= 1) {
+    // ===================== MMA issuers (warp 0 also loads the weights) =====================
+    // Two issuing warps, one per tile parity: while one of them is blocked feeding the tensor pipe with its tile's 37
+    // MMAs, the other one does the per-tile bookkeeping (barrier waits, fences, commits, block_1's MMAs) of the next
+    // tile, so the pipe does not drain between tiles (its instruction queue is only a few MMAs deep).
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(&bar_w, (uint32_t)(kW2Bytes + kW1Bytes));
+        for (int o = 0; o + 8192 <= kW2Bytes; o += 8192) bulk_load(w2s + o, (const uint8_t*)p.w2img + o, 8192, &bar_w);
+        bulk_load(w2s + 9 * 8192, (const uint8_t*)p.w2img + 9 * 8192, 2048, &bar_w);
+        bulk_load(w1s, p.w1img, kW1Bytes, &bar_w);
+      }
+      __syncwarp();
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    const int par = warp;
     mbar_wait(&bar_w, 0);
     const uint32_t hi_a1 = (128u >> 4) | (1u << 14);                  // SBO 128 B (8 rows x 16 B), version 1
     const uint32_t lo_a1_c = ((uint32_t)(kA1Rows * 16) >> 4) << 16;   // LBO 4096 B between the two K chunks
@@ -152,12 +159,10 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       __syncwarp();
     };
 
-    // Tensor-pipe order: MMA1(0) MMA1(1) | MMA2(0) MMA1(2) | MMA2(1) MMA1(3) | ...  D1(i+1) is complete before MMA2(i)
-    // starts, so E1 turns it into slab(i+1) while MMA2(i) runs, and P has two tile times to deliver A1(i+2).
-    int i = 0;
-    if ((int)blockIdx.x < n_tiles) issue_mma1(0);
-    if ((int)(blockIdx.x + gridDim.x) < n_tiles) issue_mma1(1);
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    // Per issuer: MMA1(par) | MMA2(par) MMA1(par+2) | MMA2(par+2) MMA1(par+4) | ...  block_1 of a tile is issued two
+    // tiles ahead of its block_2, so E1 turns D1(i+1) into slab(i+1) while MMA2(i) runs and P has two tile times for A1.
+    if ((int)(blockIdx.x + par * gridDim.x) < n_tiles) issue_mma1(par);
+    for (int i = par, t = blockIdx.x + par * gridDim.x; t < n_tiles; t += 2 * gridDim.x, i += 2) {
       const int stage = i % kStages, acc = i & 1;
       const uint32_t sph = (uint32_t)(i / kStages) & 1u, aph = (uint32_t)(i >> 1) & 1u;
       mbar_wait(&bar_slab_full[stage], sph);
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         const uint32_t a_lo = ((slab_addr + (uint32_t)stage * kStageBytes) >> 4) | lo_a2_c;
         const uint32_t d2 = tmem_base + (uint32_t)acc * 64;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < ((DBG & 128) ? 1 : 9); ++tap) {
           const int ky = tap / 3, kx = tap % 3;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         const int py = s / kQW, px = s - py * kQW;
         const int y = ty * kTH - 2 + py, x = tx * kTW - 2 + px;
         float v = 0.f;
-        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W && !(DBG & 1)) {
           if (j == 0) {
             v = __ldg(&img[(size_t)y * p.W + x]);
           } else {
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       //    multiply the (hi, lo) bias rows of W1.  Halo pixels outside the image get an all-zero row, so block_1's
       //    output there is exactly 0 = block_2's zero padding.
       const uint32_t one16 = p.is_bf16 ? 0x3F80u : 0x3C00u;
-      for (int r = pt; r < kHalo; r += kPThreads) {
+      for (int r = pt; r < ((DBG & 2) ? 0 : kHalo); r += kPThreads) {
         const int hy = r / kPW, hx = r - hy * kPW;
         const int gy = ty * kTH - 1 + hy, gx = tx * kTW - 1 + hx;
         uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
@@ -266,10 +271,12 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         const int r = h * 128 + q * 32 + lane;
         uint32_t v[64];
         const uint32_t taddr = tmem_base + 128 + (uint32_t)(b * 2 + h) * 64 + ((uint32_t)(q * 32) << 16);
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + 32, v + 32);
-        tmem_ld_wait();
-        if (r < kHalo) {  // bias is already inside D1 (ones columns of A1): ReLU + 16-bit pack + 8 x 16-byte stores
+        if (!(DBG & 8)) {
+          tmem_ld32(taddr, v);
+          tmem_ld32(taddr + 32, v + 32);
+          tmem_ld_wait();
+        }
+        if (r < kHalo && !(DBG & 4)) {  // bias is already inside D1 (ones columns of A1): ReLU + 16-bit pack + 8 x 16-byte stores
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8) {
             uint32_t w[4];
@@ -303,11 +310,14 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       tc_fence_after();
       uint32_t v[64];
       const uint32_t taddr = tmem_base + (uint32_t)acc * 64 + ((uint32_t)(q * 32) << 16);
-      tmem_ld32(taddr, v);
-      tmem_ld32(taddr + 32, v + 32);
-      tmem_ld_wait();
+      if (!(DBG & 64)) {
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + 32, v + 32);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       mbar_arrive(&bar_d2_empty[acc]);
+      if (DBG & 32) continue;
       uint32_t h2[32];
 #pragma unroll
       for (int c = 0; c < 32; ++c) h2[c] = pack2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]), p.is_bf16);
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 1), p.is_bf16);
         h2[c] = max2(max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 8), p.is_bf16), 0u, p.is_bf16);
       }
-      if (y < p.H && x < p.W && (g & 1) == 0 && (r & 1) == 0) {
+      if (y < p.H && x < p.W && (g & 1) == 0 && (r & 1) == 0 && !(DBG & 16)) {
         uint4* o = reinterpret_cast<uint4*>(p.out);
         const int oy = y >> 1, ox = x >> 1;
 #pragma unroll
@@ -351,11 +361,29 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
   p.w1img = w1img; p.w2img = L2.w16[bf];
   p.out = d_out;
   const size_t dyn = (size_t)kW2Bytes + kW1Bytes + kNA1 * kA1Bytes + kOnesBytes + (size_t)kStages * kStageBytes + 1024;
-  SPN_CUDA(cudaFuncSetAttribute(front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   const long long tiles = (long long)n_slots * p.tiles_x * p.tiles_y;
   const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  const int dbg = getenv("SPN_FRONT_DBG") ? atoi(getenv("SPN_FRONT_DBG")) : 0;
+  void (*kern)(const FrontParams) = front_tc_kernel<0>;
+  switch (dbg) {
+    case 0: break;
+#ifdef SPN_FRONT_DBG_BUILD
+    case 3: kern = front_tc_kernel<3>; break;
+    case 12: kern = front_tc_kernel<12>; break;
+    case 16: kern = front_tc_kernel<16>; break;
+    case 32: kern = front_tc_kernel<32>; break;
+    case 96: kern = front_tc_kernel<96>; break;
+    case 128: kern = front_tc_kernel<128>; break;
+    case 15: kern = front_tc_kernel<15>; break;
+    case 108: kern = front_tc_kernel<108>; break;
+    case 99: kern = front_tc_kernel<99>; break;
+    case 111: kern = front_tc_kernel<111>; break;
+#endif
+    default: spn_set_error("SPN_FRONT_DBG=%d is not compiled in", dbg); return SPN_E_INVALID;
+  }
+  SPN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   SpnProfScope prof(ctx, SPN_L_BLOCK2, s);
-  SPN_CUDA(spn_launch_pdl(front_tc_kernel, dim3(grid), dim3(kThreads), dyn, s, p));
+  SPN_CUDA(spn_launch_pdl(kern, dim3(grid), dim3(kThreads), dyn, s, p));
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }
