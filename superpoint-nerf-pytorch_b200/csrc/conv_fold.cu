@@ -113,6 +113,10 @@ conv_fold_kernel(const __grid_constant__ CUtensorMap tmap, const FoldParams p) {
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // The tensor pipe's instruction queue is only a few MMAs deep, so whatever the issuing warp does between two
+    // MMAs beyond that depth leaves the pipe idle.  The waits for the NEXT unit (a unit = one 64-channel block of one
+    // tile = 12 MMAs) are therefore taken in the middle of the current unit's MMAs, and the commits at its end:
+    // two short bookkeeping stretches per unit, each covered by the MMAs already queued.
     const uint32_t fmt = p.is_bf16 ? 1u : 0u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((192u >> 3) << 17) | ((128u >> 4) << 24);  // N 192, M 128
     const uint32_t a_hi = (128u >> 4) | (1u << 14);                 // A: SBO = 128 B (8 consecutive pixels)
@@ -121,39 +125,66 @@ conv_fold_kernel(const __grid_constant__ CUtensorMap tmap, const FoldParams p) {
     const uint32_t b_lo_c = ((192u * 16u) >> 4) << 16;              //    LBO = 3072 B between the two K chunks
     const uint32_t o_lo = (smem_u32(ones) >> 4) | ((2048u >> 4) << 16);
     mbar_wait(&bar_w, 0);
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
     const uint32_t w_addr = smem_u32(wsm), slab_addr = smem_u32(slab0);
-    for (int t = cta_in_slice; t < n_tiles; t += ctas_per_slice) {
-      mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+    const int my_tiles = cta_in_slice < n_tiles ? (n_tiles - cta_in_slice + ctas_per_slice - 1) / ctas_per_slice : 0;
+    const int n_units = my_tiles * p.cin_blocks;
+    int stage = 0, i = 0, cb = 0;
+    uint32_t phase = 0;
+    if (n_units > 0) {
+      mbar_wait(&bar_tempty[0], 1u);
+      mbar_wait(&bar_full[0], 0u);
       tc_fence_after();
+    }
+    for (int u = 0; u < n_units; ++u) {
+      const int acc = i & 1;
+      const bool last_cb = cb == p.cin_blocks - 1;
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * 192;
-      for (int cb = 0; cb < p.cin_blocks; ++cb) {
-        mbar_wait(&bar_full[stage], phase);
-        tc_fence_after();
-        const uint32_t a_lo = ((slab_addr + (uint32_t)stage * kSlabBytes) >> 4) | a_lo_c;
-        const uint32_t b_lo = ((w_addr + (uint32_t)cb * (12 * kBlkBytes)) >> 4) | b_lo_c;
-        if (elect_one()) {
+      const uint32_t a_lo = ((slab_addr + (uint32_t)stage * kSlabBytes) >> 4) | a_lo_c;
+      const uint32_t b_lo = ((w_addr + (uint32_t)cb * (12 * kBlkBytes)) >> 4) | b_lo_c;
+      if (elect_one()) {
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t aoff = ((uint32_t)ky * (kTWs * 16) + (uint32_t)kk * 2 * kChStride) >> 4;
-              const uint32_t boff = ((uint32_t)(ky * 4 + kk) * kBlkBytes) >> 4;
-              umma_f16_2w(d_tmem, a_lo + aoff, a_hi, b_lo + boff, b_hi, idesc, (cb | ky | kk) ? 1u : 0u);
-            }
-          }
-          umma_commit(&bar_empty[stage]);
-          if (cb == p.cin_blocks - 1) {
-            const uint32_t bb_lo = ((w_addr + (uint32_t)p.cin_blocks * (12 * kBlkBytes)) >> 4) | b_lo_c;
-            umma_f16_2w(d_tmem, o_lo, a_hi, bb_lo, b_hi, idesc, 1u);  // + bias (lives in the kx = 1 column block)
-            umma_commit(&bar_tfull[acc]);
-          }
+        for (int m = 0; m < 8; ++m) {
+          const int ky = m >> 2, kk = m & 3;
+          const uint32_t aoff = ((uint32_t)ky * (kTWs * 16) + (uint32_t)kk * 2 * kChStride) >> 4;
+          const uint32_t boff = ((uint32_t)(ky * 4 + kk) * kBlkBytes) >> 4;
+          umma_f16_2w(d_tmem, a_lo + aoff, a_hi, b_lo + boff, b_hi, idesc, (cb | m) ? 1u : 0u);
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      __syncwarp();
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == p.stages) { nstage = 0; nphase ^= 1u; }
+      if (u + 1 < n_units) {  // the next unit's operands and accumulator, while 8 MMAs are in the queue
+        // With 128 input channels a tile is 25 MMAs and the kernel is tensor-bound: take the accumulator wait here too.
+        // With 64 it is bound by the epilogues' TMEM reads (96 KB per tile against 13 MMAs): the accumulator of tile
+        // i+1 is usually not free yet, so tile i is issued completely first (its epilogue can then start at once).
+        if (last_cb && p.cin_blocks > 1) mbar_wait(&bar_tempty[(i + 1) & 1], ((uint32_t)((i + 1) >> 1) & 1u) ^ 1u);
+        mbar_wait(&bar_full[nstage], nphase);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+#pragma unroll
+        for (int m = 8; m < 12; ++m) {
+          const int ky = m >> 2, kk = m & 3;
+          const uint32_t aoff = ((uint32_t)ky * (kTWs * 16) + (uint32_t)kk * 2 * kChStride) >> 4;
+          const uint32_t boff = ((uint32_t)(ky * 4 + kk) * kBlkBytes) >> 4;
+          umma_f16_2w(d_tmem, a_lo + aoff, a_hi, b_lo + boff, b_hi, idesc, 1u);
+        }
+        umma_commit(&bar_empty[stage]);
+        if (last_cb) {
+          const uint32_t bb_lo = ((w_addr + (uint32_t)p.cin_blocks * (12 * kBlkBytes)) >> 4) | b_lo_c;
+          umma_f16_2w(d_tmem, o_lo, a_hi, bb_lo, b_hi, idesc, 1u);  // + bias (lives in the kx = 1 column block)
+          umma_commit(&bar_tfull[acc]);
+        }
+      }
+      __syncwarp();
+      if (u + 1 < n_units && last_cb && p.cin_blocks == 1) {
+        mbar_wait(&bar_tempty[(i + 1) & 1], ((uint32_t)((i + 1) >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+      }
+      stage = nstage;
+      phase = nphase;
+      if (last_cb) { cb = 0; ++i; } else { ++cb; }
     }
   } else {
     // ===================== epilogue: group 0 (warps 2-5) takes even tiles, group 1 (warps 6-9) odd tiles =====================
