@@ -109,7 +109,9 @@ SPN_API int spn_sample_descriptors(spn_ctx* ctx, const float* d_desc_raw, int B,
 
 /* box_nms (sp_utils.py:4-28) + threshold (heads.py:41 / export.py:123) + nonzero (export.py:125), batched.
  * d_prob [B][H][W]; outputs (each nullable): d_nms [B][H][W] fp32, d_pred [B][H][W] int32 (= nms >= det_thresh),
- * d_kp [B][max_kp][2] int32 (row, col) in row-major order, d_kp_count [B] (true count, may exceed max_kp). */
+ * d_kp [B][max_kp][2] int32 (row, col) in row-major order, d_kp_count [B] (true count, may exceed max_kp).
+ * 0 < size <= 8; box sizes up to 4 (the reference default) take the bit-plane kernel, larger ones the generic one;
+ * the result is bit-identical to torchvision.ops.nms on the same heatmap either way. */
 SPN_API int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H, int W, float size, float iou, float min_prob,
                      int top_k, float det_thresh, float* d_nms, int32_t* d_pred, int32_t* d_kp, int32_t* d_kp_count,
                      int max_kp, spn_stream stream);
@@ -124,7 +126,8 @@ SPN_API int spn_nms_stats(spn_ctx* ctx, int B, int H, int W, int64_t* h_out);
  *   slot = i*(n_h+1)         : the image itself, mask = 1 (identity forward, export.py:93)
  * d_hinv [n_images][n_h][9] fp32 are the pixel-space INVERSES of the matrices the reference passes
  * (kornia samples src at M^-1 p).  d_images [n_images][H][W]; d_warped [n_images*(n_h+1)][H][W] fp32;
- * d_mask same shape u8.  d_warped may be NULL (mask only: the fused encoder spn_encoder_forward_ha warps on the fly). */
+ * d_mask same shape u8.  d_warped may be NULL (mask only: the fused encoder spn_encoder_forward_ha warps on the fly).
+ * Limits: 1 <= margin <= 8, n_images*(n_h+1) <= 65535 per call, W <= 8192. */
 SPN_API int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H, int W,
                    int margin, float* d_warped, uint8_t* d_mask, spn_stream stream);
 
@@ -132,7 +135,8 @@ SPN_API int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, co
  * for every image: out(p) = [ prob_0(p) + sum_j count_j(p) * bilinear(prob_j, H_j p) ] / [ 1 + sum_j count_j(p) ]
  * with count_j = erosion(nearest warp of ones by H_j^-1)  (aggregation 0 = 'sum'), or the max over the same
  * terms (aggregation 1 = 'max').  d_probs [n_images][n_h+1][H][W] (already multiplied by the masks),
- * d_h [n_images][n_h][9] fp32 pixel-space H as the reference samples them; d_out [n_images][H][W]. */
+ * d_h [n_images][n_h][9] fp32 pixel-space H as the reference samples them; d_out [n_images][H][W].
+ * Limits: 1 <= margin <= 8, n_h <= 255, (n_h+1)*H*W < 2^30. */
 SPN_API int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float* d_h, int n_images, int n_h, int H, int W,
                      int margin, int aggregation, float* d_out, spn_stream stream);
 
