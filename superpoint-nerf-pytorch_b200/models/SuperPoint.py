@@ -8,6 +8,7 @@ Inference only (the reference's export tasks call ``model.eval()``, export.py:21
 Extension keys (all optional) in the ``model`` config: ``precision`` in {'fp32','f16','bf16'} (default from
 $SPN_B200_PRECISION, else 'fp32'), ``dense_desc`` (default True, as the reference).
 """
+import itertools
 import os
 
 import torch
@@ -72,7 +73,9 @@ class SuperPoint(nn.Module):
 
     # ---- native state ----------------------------------------------------------------------------
     def _weights_key(self):
-        return tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict(keep_vars=True).items())
+        # (version counter, storage address) of every parameter and buffer: changes whenever load_state_dict / an
+        # in-place update / .to() touches the weights, without building a state_dict on every call
+        return tuple((v._version, v.data_ptr()) for v in itertools.chain(self.parameters(), self.buffers()))
 
     def native(self, slot: int = 0) -> Context:
         """The Context holding this model's packed weights (re-packed when parameters change).  Each ``slot`` is an
