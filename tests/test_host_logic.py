@@ -128,3 +128,38 @@ def test_preprocessing_host_side_matches_reference(golden):
                 if 0 <= ry < nh and 0 <= rx < nw:
                     got[y, x] = probe[ry, rx]
         assert torch.equal(got, want), (src, tgt)
+
+
+def test_npz_writer_pool_is_transparent(tmp_path):
+    """The HPatches exports hand np.savez_compressed to a bounded thread pool: same bytes as a synchronous save, bounded
+    number of files in flight, and a writer's exception surfaces in the caller."""
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import _NpzWriter
+    rng = np.random.RandomState(3)
+    items = [{"image": rng.rand(24, 32).astype(np.float32), "prob": rng.rand(24, 32).astype(np.float32),
+              "homography": np.eye(3, dtype=np.float32) * (k + 1)} for k in range(9)]
+    w = _NpzWriter(workers=3, depth=4)
+    for k, it in enumerate(items):
+        w.save(tmp_path / f"a{k}.npz", it)
+        assert len(w.pending) <= 4
+    w.close()
+    for k, it in enumerate(items):
+        np.savez_compressed(tmp_path / f"b{k}.npz", **it)
+        assert (tmp_path / f"a{k}.npz").read_bytes() == (tmp_path / f"b{k}.npz").read_bytes()
+    w = _NpzWriter(workers=1, depth=1)
+    w.save(tmp_path / "missing_dir" / "x.npz", items[0])
+    with pytest.raises(Exception):
+        w.close()
+
+
+def test_weights_key_tracks_parameter_updates():
+    """The packed-weight cache key must change when weights are loaded or modified in place."""
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    m = get_model(MP_MODEL, "cpu")
+    k0 = m._weights_key()
+    assert m._weights_key() == k0
+    m.load_state_dict(O.make_state_dict("magicpoint", seed=1))
+    k1 = m._weights_key()
+    assert k1 != k0
+    with torch.no_grad():
+        m.detector_head.convPb.conv2d.bias.add_(1.0)
+    assert m._weights_key() != k1
