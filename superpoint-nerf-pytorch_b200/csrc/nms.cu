@@ -50,24 +50,6 @@ __device__ __forceinline__ uint32_t ordered_key(float f) {  // monotone float ->
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// exclusive prefix of `flag` over the 1024 threads in thread order; *total gets the block sum. 2 barriers.
-__device__ __forceinline__ int block_excl_scan_flag(bool flag, int* s_warp, int* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned bal = __ballot_sync(0xffffffffu, flag);
-  const int within = __popc(bal & ((1u << lane) - 1u));
-  if (lane == 0) s_warp[warp] = __popc(bal);
-  __syncthreads();
-  int base = 0, tot = 0;
-  for (int w = 0; w < kThreads / 32; ++w) {
-    const int c = s_warp[w];
-    if (w < warp) base += c;
-    tot += c;
-  }
-  __syncthreads();
-  *total = tot;
-  return base + within;
-}
-
 // Phase 1: greedy NMS as a parallel fixed point, all SMs cooperating on the whole batch.
 // Work unit = 32x32 pixel tile (one thread per pixel) with a halo of `foot.r` pixels staged in shared memory
 // (scores + status bytes, coalesced loads).  Inside a tile the rule is iterated to a local fixed point with the halo
@@ -394,20 +376,33 @@ nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ st
         want = s_sel[1];
         __syncthreads();
       }
-      // prefix = key of the top_k-th survivor; keep keys > prefix, and the first `want` equal keys in index order
+      // prefix = key of the top_k-th survivor; keep keys > prefix, and the first `want` equal keys in index order.
+      // Warp w owns the contiguous pixel range [w*seg, (w+1)*seg): count its ties (no barriers), one block scan over the
+      // 32 warps, then walk the range in order with ballot ranks.
+      const int lane_t = tid & 31, warp_t = tid >> 5;
+      const int seg_t = ((P + kThreads - 1) / kThreads) * 32;
+      const int tb = warp_t * seg_t, te = min(P, tb + seg_t);
+      int tcnt = 0;
+      for (int p = tb + lane_t; p < te; p += 32) {
+        if (status[p] != 2) continue;
+        const uint32_t key = ordered_key(__ldg(&prob[p]));
+        if (key < prefix) status[p] = 0;
+        tcnt += (key == prefix);
+      }
+      for (int o = 16; o > 0; o >>= 1) tcnt += __shfl_xor_sync(0xffffffffu, tcnt, o);
+      __syncthreads();
+      if (lane_t == 0) s_warp[warp_t] = tcnt;
+      __syncthreads();
       int tie_base = 0;
-      for (int base = 0; base < P; base += kThreads) {
-        const int p = base + tid;
-        bool tie = false;
-        if (p < P && status[p] == 2) {
-          const uint32_t key = ordered_key(__ldg(&prob[p]));
-          if (key < prefix) status[p] = 0;
-          tie = (key == prefix);
+      for (int w = 0; w < warp_t; ++w) tie_base += s_warp[w];
+      if (tcnt > 0) {  // warp-uniform
+        for (int p0 = tb; p0 < te; p0 += 32) {
+          const int p = p0 + lane_t;
+          const bool tie = p < te && status[p] == 2 && ordered_key(__ldg(&prob[p])) == prefix;
+          const unsigned bal = __ballot_sync(0xffffffffu, tie);
+          if (tie && (unsigned)(tie_base + __popc(bal & ((1u << lane_t) - 1u))) >= want) status[p] = 0;
+          tie_base += __popc(bal);
         }
-        int tot;
-        const int rank = block_excl_scan_flag(tie, s_warp, &tot);
-        if (tie && (unsigned)(tie_base + rank) >= want) status[p] = 0;
-        tie_base += tot;
       }
       __syncthreads();
     }

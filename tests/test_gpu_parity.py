@@ -406,6 +406,33 @@ def test_sparse_descriptors_bilinear_and_bicubic_vs_torch(ctx):
         assert np.all(got[1, 150:] == 0)        # slots beyond kp_count stay zero
 
 
+@pytest.mark.parametrize("shape,grid", [((2, 256, 15, 20), 8), ((1, 64, 9, 9), 8), ((1, 32, 7, 13), 4), ((1, 16, 5, 40), 2),
+                                        ((1, 8, 6, 37), 1)])
+def test_dense_descriptors_vs_torch(ctx, shape, grid):
+    """spn_dense_descriptors (separable kernel for grid >= 2, direct kernel for grid 1; widths that are not multiples
+    of the 32-pixel block) vs F.interpolate(bicubic, align_corners=False) + F.normalize (heads.py:65-66)."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(sum(shape) + grid)
+    raw = torch.from_numpy(rng.randn(*shape).astype(np.float32))
+    want = F.normalize(F.interpolate(raw, scale_factor=grid, mode="bicubic", align_corners=False), p=2, dim=1).numpy()
+    got = ctx.dense_descriptors(raw.cuda(), grid).cpu().numpy()
+    assert got.shape == want.shape
+    assert rel_err(got, want) < STRICT
+    assert np.abs(np.linalg.norm(got, axis=1) - 1).max() < 1e-5
+
+
+def test_box_nms_topk_with_many_ties(ctx):
+    """top-k where the k-th score is shared by many pixels spread over the whole image: the tie break (lower row-major
+    index first) runs through the warp-segment ranking of nms_finalize_kernel."""
+    rng = np.random.RandomState(11)
+    for (h, w, k) in [(240, 320, 300), (480, 640, 1000), (37, 53, 40)]:
+        p = (np.round(rng.rand(h, w) * 3) / 3 * 0.5 + 0.25).astype(np.float32)   # four distinct values
+        want = O.box_nms_c(p, 4, 0.1, 0.2, k).numpy()
+        r = ctx.box_nms(torch.from_numpy(p).cuda().unsqueeze(0), 4, 0.1, 0.2, k, det_thresh=0.2, want_map=True, max_kp=h * w)
+        assert np.array_equal(r["nms"][0].cpu().numpy(), want)
+        assert int(r["kp_count"][0]) == int((want >= 0.2).sum()) <= k
+
+
 def test_preprocessing_kernel_vs_reference(ctx, golden):
     """spn_resize_crop (uint8 and fp32 sources) vs the reference loader's ratio_preserving_resize + /255."""
     from superpoint_nerf_pytorch_b200.data.preprocessing import ratio_preserving_resize
