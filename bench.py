@@ -130,8 +130,13 @@ def cpu_reference_sample(n_hom: int, threads: int | None = None):
 
     from oracle import spn_oracle as O
 
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:
+        # every host core this process may use (torchrun exports OMP_NUM_THREADS=1, which would make it a 1-thread run)
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, threads))
     cfg = {"homography_adaptation": dict(copy.deepcopy(HA_CFG), num=n_hom), "model": copy.deepcopy(MODEL_CFG)}
     sd = random_init_state_dict()  # the same random-init weights the native arm runs (flat ~1/65 heatmap)
     g = torch.Generator().manual_seed(0)
