@@ -326,7 +326,8 @@ nms_rounds_bits_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__
 __global__ void __launch_bounds__(kThreads)
 nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ status_all, int H, int W, int top_k,
                     float det_thresh, float* __restrict__ nms_all, int32_t* __restrict__ pred_all,
-                    int32_t* __restrict__ kp_all, int32_t* __restrict__ kp_count, int max_kp) {
+                    int32_t* __restrict__ kp_all, int32_t* __restrict__ kp_count, int max_kp,
+                    uint32_t* __restrict__ list_all) {
   __shared__ int s_warp[kThreads / 32];
   __shared__ unsigned s_hist[256];
   __shared__ unsigned s_sel[2];
@@ -337,26 +338,46 @@ nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ st
   const int tid = threadIdx.x;
 
   // ---- optional top-k over the survivors: (score desc, index asc) ----
+  // The survivors (a few percent of the pixels) are first compacted, in index order, into a (key, index) list; the
+  // radix select and the tie ranking then walk that list instead of the whole image.
   if (top_k > 0) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int seg = ((P + kThreads - 1) / kThreads) * 32;  // warp w owns pixels [w*seg, (w+1)*seg)
+    const int pb = warp * seg, pe = min(P, pb + seg);
     int mine = 0;
-    for (int p = tid; p < P; p += kThreads) mine += (status[p] == 2);
-    // block sum of kept
+    for (int p = pb + lane; p < pe; p += 32) mine += (status[p] == 2);
     for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if ((tid & 31) == 0) s_warp[tid >> 5] = mine;
+    if (lane == 0) s_warp[warp] = mine;
     __syncthreads();
-    int kept = 0;
-    for (int w = 0; w < kThreads / 32; ++w) kept += s_warp[w];
+    int kept = 0, base = 0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      if (w < warp) base += s_warp[w];
+      kept += s_warp[w];
+    }
     __syncthreads();
     if (kept > top_k) {
+      uint32_t* lkey = list_all + (size_t)b * 2 * P;   // [kept] ordered keys
+      int32_t* lidx = reinterpret_cast<int32_t*>(lkey + P);  // [kept] pixel indices, ascending
+      for (int p0 = pb; p0 < pe; p0 += 32) {
+        const int p = p0 + lane;
+        const bool k2 = p < pe && status[p] == 2;
+        const unsigned bal = __ballot_sync(0xffffffffu, k2);
+        if (k2) {
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          lkey[pos] = ordered_key(__ldg(&prob[p]));
+          lidx[pos] = p;
+        }
+        base += __popc(bal);
+      }
+      __syncthreads();  // list complete (block-scope visibility of the global writes)
       uint32_t prefix = 0, maskbits = 0;
       unsigned want = (unsigned)top_k;  // rank (1-based, descending) of the threshold element
       for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         if (tid < 256) s_hist[tid] = 0;
         __syncthreads();
-        for (int p = tid; p < P; p += kThreads) {
-          if (status[p] != 2) continue;
-          const uint32_t key = ordered_key(__ldg(&prob[p]));
+        for (int i = tid; i < kept; i += kThreads) {
+          const uint32_t key = lkey[i];
           if ((key & maskbits) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
@@ -376,31 +397,27 @@ nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ st
         want = s_sel[1];
         __syncthreads();
       }
-      // prefix = key of the top_k-th survivor; keep keys > prefix, and the first `want` equal keys in index order.
-      // Warp w owns the contiguous pixel range [w*seg, (w+1)*seg): count its ties (no barriers), one block scan over the
-      // 32 warps, then walk the range in order with ballot ranks.
-      const int lane_t = tid & 31, warp_t = tid >> 5;
-      const int seg_t = ((P + kThreads - 1) / kThreads) * 32;
-      const int tb = warp_t * seg_t, te = min(P, tb + seg_t);
+      // prefix = key of the top_k-th survivor; keep keys > prefix and the first `want` equal keys in index order.
+      // Warp w owns list positions [w*lseg, (w+1)*lseg): count its ties, one block scan, then rank them in order.
+      const int lseg = ((kept + kThreads - 1) / kThreads) * 32;
+      const int lb = min(kept, warp * lseg), le = min(kept, lb + lseg);
       int tcnt = 0;
-      for (int p = tb + lane_t; p < te; p += 32) {
-        if (status[p] != 2) continue;
-        const uint32_t key = ordered_key(__ldg(&prob[p]));
-        if (key < prefix) status[p] = 0;
+      for (int i = lb + lane; i < le; i += 32) {
+        const uint32_t key = lkey[i];
+        if (key < prefix) status[lidx[i]] = 0;
         tcnt += (key == prefix);
       }
       for (int o = 16; o > 0; o >>= 1) tcnt += __shfl_xor_sync(0xffffffffu, tcnt, o);
-      __syncthreads();
-      if (lane_t == 0) s_warp[warp_t] = tcnt;
+      if (lane == 0) s_warp[warp] = tcnt;
       __syncthreads();
       int tie_base = 0;
-      for (int w = 0; w < warp_t; ++w) tie_base += s_warp[w];
+      for (int w = 0; w < warp; ++w) tie_base += s_warp[w];
       if (tcnt > 0) {  // warp-uniform
-        for (int p0 = tb; p0 < te; p0 += 32) {
-          const int p = p0 + lane_t;
-          const bool tie = p < te && status[p] == 2 && ordered_key(__ldg(&prob[p])) == prefix;
+        for (int i0 = lb; i0 < le; i0 += 32) {
+          const int i = i0 + lane;
+          const bool tie = i < le && lkey[i] == prefix;
           const unsigned bal = __ballot_sync(0xffffffffu, tie);
-          if (tie && (unsigned)(tie_base + __popc(bal & ((1u << lane_t) - 1u))) >= want) status[p] = 0;
+          if (tie && (unsigned)(tie_base + __popc(bal & ((1u << lane) - 1u))) >= want) status[lidx[i]] = 0;
           tie_base += __popc(bal);
         }
       }
@@ -493,11 +510,14 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
   int tiles_x = spn_cdiv(W, 32), tiles_y = spn_cdiv(H, 32);
   const long long n_tiles = (long long)B * tiles_x * tiles_y;
   SPN_REQUIRE(n_tiles < (1ll << 28), "spn_box_nms_topk: batch too large");
-  int rc = spn_ensure_aux(ctx, status_bytes + 256 + 2 * (size_t)n_tiles * sizeof(int), s);
+  const size_t lists_bytes = (2 * (size_t)n_tiles * sizeof(int) + 255) & ~(size_t)255;
+  const size_t topk_bytes = top_k > 0 ? (size_t)B * H * W * 8 : 0;   // (key, index) list of the survivors, per image
+  int rc = spn_ensure_aux(ctx, status_bytes + 256 + lists_bytes + topk_bytes, s);
   if (rc) return rc;
   uint8_t* status = (uint8_t*)ctx->aux;
   unsigned* pend = (unsigned*)(ctx->aux + status_bytes);
   int* lists = (int*)(ctx->aux + status_bytes + 256);
+  uint32_t* topk_list = top_k > 0 ? (uint32_t*)(ctx->aux + status_bytes + 256 + lists_bytes) : nullptr;
   const bool bits_path = foot.r >= 1 && foot.r <= 3;  // box sizes up to 4: bit-plane kernel
   uint32_t foot_lo = 0, foot_hi = 0;
   if (bits_path)
@@ -526,7 +546,8 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
     SPN_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), args, smem, s));
   }
   ctx->launches++;
-  nms_finalize_kernel<<<B, kThreads, 0, s>>>(d_prob, status, H, W, top_k, det_thresh, d_nms, d_pred, d_kp, d_kp_count, max_kp);
+  nms_finalize_kernel<<<B, kThreads, 0, s>>>(d_prob, status, H, W, top_k, det_thresh, d_nms, d_pred, d_kp, d_kp_count, max_kp,
+                                             topk_list);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }
