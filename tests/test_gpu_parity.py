@@ -54,7 +54,10 @@ def test_box_nms_golden_bit_exact(ctx, golden):
 @pytest.mark.parametrize("shape,size,min_prob,topk,kind", [
     ((240, 320), 4, 0.015, 0, "flat"), ((480, 640), 4, 0.001, 1000, "flat"), ((120, 160), 4, 0.001, 0, "flat"),
     ((240, 320), 8, 0.1, 300, "uniform"), ((96, 128), 3, 0.2, 0, "ties"), ((64, 512), 4, 0.0, 0, "ramp"),
-    ((8, 8), 4, 0.5, 3, "uniform"), ((240, 320), 4, 2.0, 5, "uniform")])
+    ((8, 8), 4, 0.5, 3, "uniform"), ((240, 320), 4, 2.0, 5, "uniform"),
+    # footprint radius 1 and 2 (templated bit-plane kernels), radius 0 (no neighbour suppresses) and fractional sizes
+    ((64, 96), 2, 0.3, 0, "uniform"), ((70, 50), 2, 0.0, 25, "ties"), ((64, 96), 1, 0.3, 10, "uniform"),
+    ((50, 70), 2.5, 0.2, 0, "ties"), ((33, 65), 3.5, 0.1, 0, "flat")])
 def test_box_nms_vs_oracle(ctx, shape, size, min_prob, topk, kind):
     rng = np.random.RandomState(hash((shape, size, kind)) % 2**31)
     h, w = shape
