@@ -81,9 +81,9 @@ SPN_API int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, int 
 /* Fused K.warp_perspective(image, H) (export.py:51) + VGG_BACKBONE.forward for the homography-adaptation slots
  * slot = i*(n_h+1) + j (j == 0: image i itself, j >= 1: image i warped by homography j-1) with
  * slot_begin <= slot < slot_begin + n_slots; tensor-core modes only.  The warped images are never written to memory:
- * the warp is evaluated inside the first convolution kernel.  d_images [n_images][H][W], d_hinv [n_images][n_h][9]
- * (pixel-space inverses, as for spn_warp_batch).  Leaves the feature map of the n_slots forwards inside ctx. */
-SPN_API int spn_encoder_forward_ha(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h,
+ * the warp is evaluated inside the first convolution kernel.  d_images [n_images][H][W], d_ainv [n_images][n_h][9]
+ * (kornia sampling matrices, as for spn_warp_batch).  Leaves the feature map of the n_slots forwards inside ctx. */
+SPN_API int spn_encoder_forward_ha(spn_ctx* ctx, const float* d_images, int n_images, const float* d_ainv, int n_h,
                                    int slot_begin, int n_slots, int H, int W, int mode, spn_stream stream);
 
 /* Detector_head.forward up to prob_heatmap (heads.py:17-28): convPa, convPb, softmax(65), drop dustbin,
@@ -124,20 +124,26 @@ SPN_API int spn_nms_stats(spn_ctx* ctx, int B, int H, int W, int64_t* h_out);
  *   slot = i*(n_h+1) + 1 + j : d_warped[slot] = warp_perspective(image_i, H_ij, bilinear, align_corners=True)
  *                              d_mask[slot]   = erosion(warp_perspective(ones, H_ij, nearest), ellipse(2*margin))
  *   slot = i*(n_h+1)         : the image itself, mask = 1 (identity forward, export.py:93)
- * d_hinv [n_images][n_h][9] fp32 are the pixel-space INVERSES of the matrices the reference passes
- * (kornia samples src at M^-1 p).  d_images [n_images][H][W]; d_warped [n_images*(n_h+1)][H][W] fp32;
- * d_mask same shape u8.  d_warped may be NULL (mask only: the fused encoder spn_encoder_forward_ha warps on the fly).
- * Limits: 1 <= margin <= 8, n_images*(n_h+1) <= 65535 per call, W <= 8192. */
-SPN_API int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H, int W,
+ * d_ainv [n_images][n_h][9] fp32 are kornia's sampling matrices of H_ij in NORMALISED coordinates,
+ *   Ainv = torch.inverse(normalize_homography(H_ij, (H,W), (H,W)))      (what K.warp_perspective builds internally),
+ * the "fwd" output of spn_kornia_matrices.  The kernel follows kornia's fp32 coordinate chain operation for operation
+ * (create_meshgrid -> bmm -> 1/(z+1e-8) -> grid_sample unnormalise / nearbyint / ATen bilinear weights), so masks and
+ * warped pixels are BIT-IDENTICAL to the reference's CPU run when Ainv carries the reference's bits.
+ * d_images [n_images][H][W]; d_warped [n_images*(n_h+1)][H][W] fp32; d_mask same shape u8.  d_warped may be NULL
+ * (mask only: the fused encoder spn_encoder_forward_ha warps on the fly).
+ * Limits: 1 <= margin <= 8, n_images*(n_h+1) <= 65535 per call, W <= 8192, H, W >= 2. */
+SPN_API int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_ainv, int n_h, int H, int W,
                    int margin, float* d_warped, uint8_t* d_mask, spn_stream stream);
 
 /* ExportDetections.step projection + homography_adaptation aggregation (export.py:72-77,106-114):
  * for every image: out(p) = [ prob_0(p) + sum_j count_j(p) * bilinear(prob_j, H_j p) ] / [ 1 + sum_j count_j(p) ]
  * with count_j = erosion(nearest warp of ones by H_j^-1)  (aggregation 0 = 'sum'), or the max over the same
  * terms (aggregation 1 = 'max').  d_probs [n_images][n_h+1][H][W] (already multiplied by the masks),
- * d_h [n_images][n_h][9] fp32 pixel-space H as the reference samples them; d_out [n_images][H][W].
+ * d_ainv_bwd [n_images][n_h][9] fp32 = kornia's sampling matrices of the INVERSE homographies,
+ *   torch.inverse(normalize_homography(torch.inverse(H_ij)))            (export.py:49,55,72),
+ * the "bwd" output of spn_kornia_matrices; same bit-exact coordinate chain as spn_warp_batch.  d_out [n_images][H][W].
  * Limits: 1 <= margin <= 8, n_h <= 255, (n_h+1)*H*W < 2^30. */
-SPN_API int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float* d_h, int n_images, int n_h, int H, int W,
+SPN_API int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float* d_ainv_bwd, int n_images, int n_h, int H, int W,
                      int margin, int aggregation, float* d_out, spn_stream stream);
 
 /* Homographic_aug.sample_homography (data/data_utils/homographic_augmentation.py:21-106) on the device:
@@ -152,6 +158,14 @@ typedef struct spn_homography_params {
 } spn_homography_params;
 SPN_API int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params* params, uint64_t seed, uint64_t first_index,
                             int count, int H, int W, float* d_h, float* d_hinv, spn_stream stream);
+
+/* kornia.geometry normalize_homography + torch.inverse for a batch of pixel-space homographies d_h [count][9]
+ * (the matrices K.warp_perspective derives at export.py:51-55,72): d_ainv_fwd = inverse(N (H N^-1)) and d_ainv_bwd =
+ * the same for H^-1, N = normal_transform_pixel(H, W).  Device arithmetic (adjugate inverse): equal to the reference's
+ * LAPACK inverse to a few ulp, not bit for bit - callers that need bit-identical masks pass matrices computed with the
+ * reference's own torch calls (the Python binding does so whenever the homographies come from the host). */
+SPN_API int spn_kornia_matrices(spn_ctx* ctx, const float* d_h, int count, int H, int W, float* d_ainv_fwd, float* d_ainv_bwd,
+                                spn_stream stream);
 
 /* Loader pre-processing of one decoded grayscale image (data/COCO.py:66-76 ratio_preserving_resize + the /255 of
  * COCO.py:135; data/HPatches.py:64-72): bilinear resize to new_h x new_w (align_corners=False, as kornia.resize ->

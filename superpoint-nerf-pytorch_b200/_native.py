@@ -55,6 +55,7 @@ PROTOTYPES = {
     "spn_sample_homographies": (_i, [_vp, C.POINTER(HomographyParams), C.c_uint64, C.c_uint64, _i, _i, _i, _vp, _vp, _vp]),
     "spn_resize_crop": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "spn_invert3x3": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "spn_kornia_matrices": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "spn_launch_count": (C.c_int64, [_vp]),
     "spn_profile_enable": (_i, [_vp, _i]),
     "spn_profile_read": (_i, [_vp, _vp, _vp]),
@@ -96,13 +97,16 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """torch's current stream ON THE GIVEN DEVICE (not on torch's current device, which may be another GPU)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _chk_dev(t: torch.Tensor, dtype, name):
+def _chk_dev(t: torch.Tensor, dtype, name, device=None):
     if not (torch.is_tensor(t) and t.is_cuda):
         raise NativeError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if device is not None and t.device.index != device:
+        raise NativeError(f"{name} lives on cuda:{t.device.index} but this context owns cuda:{device}")
     if t.dtype != dtype:
         raise NativeError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -126,6 +130,9 @@ class Context:
         self._call("spn_create", C.byref(h), self.device)
         self.handle = h
         self._weights_key = None
+
+    def _s(self):
+        return _stream(self.device)
 
     def _call(self, name, *args):
         rc = getattr(self.lib, name)(*args)
@@ -172,81 +179,81 @@ class Context:
             g, be, mu, var = get("norm.weight"), get("norm.bias"), get("norm.running_mean"), get("norm.running_var")
             cout, cin, k, _ = w.shape
             self._call("spn_pack_weights", self.handle, lid, _ptr(w), _ptr(b), _ptr(g), _ptr(be), _ptr(mu), _ptr(var),
-                       C.c_float(eps), cout, cin, k, _stream())
+                       C.c_float(eps), cout, cin, k, self._s())
 
     def conv_layer(self, layer: int, x: torch.Tensor, mode: int, relu=True, pool=False, cout=None):
         """One VGG_Block (conv + folded BN [+ ReLU] [+ 2x2 max-pool]) on NCHW fp32 tensors."""
         x = _dense(x)
-        _chk_dev(x, torch.float32, "x")
+        _chk_dev(x, torch.float32, "x", self.device)
         B, _, H, W = x.shape
         out = torch.empty((B, cout, H // 2 if pool else H, W // 2 if pool else W), dtype=torch.float32, device=x.device)
-        self._call("spn_conv_layer", self.handle, layer, mode, _ptr(x), B, H, W, int(relu), int(pool), _ptr(out), _stream())
+        self._call("spn_conv_layer", self.handle, layer, mode, _ptr(x), B, H, W, int(relu), int(pool), _ptr(out), self._s())
         return out
 
     # ---- forward -------------------------------------------------------------------------------
     def encoder_forward(self, images: torch.Tensor, mode: int):
         images = _dense(images)
-        _chk_dev(images, torch.float32, "images")
+        _chk_dev(images, torch.float32, "images", self.device)
         B, H, W = images.shape
-        self._call("spn_encoder_forward", self.handle, _ptr(images), B, H, W, mode, _stream())
+        self._call("spn_encoder_forward", self.handle, _ptr(images), B, H, W, mode, self._s())
 
     def encoder_forward_ha(self, images: torch.Tensor, hinv, slot_begin: int, n_slots: int, mode: int):
         """Fused warp + encoder for slots [slot_begin, slot_begin+n_slots) of (images (NI,H,W), hinv (NI,n_h,3,3))."""
         images, hinv = _dense(images), _dense(hinv)
-        _chk_dev(images, torch.float32, "images")
+        _chk_dev(images, torch.float32, "images", self.device)
         NI, H, W = images.shape
         n_h = 0 if hinv is None else hinv.shape[1]
         if n_h:
-            _chk_dev(hinv, torch.float32, "hinv")
+            _chk_dev(hinv, torch.float32, "hinv", self.device)
         self._call("spn_encoder_forward_ha", self.handle, _ptr(images), NI, _ptr(hinv) if n_h else None, n_h, int(slot_begin),
-                   int(n_slots), H, W, mode, _stream())
+                   int(n_slots), H, W, mode, self._s())
 
     def detector_head_forward(self, B, H, W, mode, mask=None, want_logits=False, out=None):
         dev = torch.device("cuda", self.device)
         if out is None:
             prob = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         else:
-            _chk_dev(out, torch.float32, "out")
+            _chk_dev(out, torch.float32, "out", self.device)
             if tuple(out.shape) != (B, H, W):
                 raise NativeError(f"out must be {(B, H, W)}, got {tuple(out.shape)}")
             prob = out
         logits = torch.empty((B, 65, H // 8, W // 8), dtype=torch.float32, device=dev) if want_logits else None
         if mask is not None:
             mask = _dense(mask)
-            _chk_dev(mask, torch.uint8, "mask")
-        self._call("spn_detector_head_forward", self.handle, B, H, W, mode, _ptr(mask), _ptr(logits), _ptr(prob), _stream())
+            _chk_dev(mask, torch.uint8, "mask", self.device)
+        self._call("spn_detector_head_forward", self.handle, B, H, W, mode, _ptr(mask), _ptr(logits), _ptr(prob), self._s())
         return prob, logits
 
     def descriptor_head_forward(self, B, H, W, mode):
         raw = torch.empty((B, 256, H // 8, W // 8), dtype=torch.float32, device=torch.device("cuda", self.device))
-        self._call("spn_descriptor_head_forward", self.handle, B, H, W, mode, _ptr(raw), _stream())
+        self._call("spn_descriptor_head_forward", self.handle, B, H, W, mode, _ptr(raw), self._s())
         return raw
 
     def dense_descriptors(self, raw: torch.Tensor, grid: int):
         raw = _dense(raw)
-        _chk_dev(raw, torch.float32, "desc_raw")
+        _chk_dev(raw, torch.float32, "desc_raw", self.device)
         B, Cc, Hc, Wc = raw.shape
         out = torch.empty((B, Cc, Hc * grid, Wc * grid), dtype=torch.float32, device=raw.device)
-        self._call("spn_dense_descriptors", self.handle, _ptr(raw), B, Cc, Hc, Wc, grid, _ptr(out), _stream())
+        self._call("spn_dense_descriptors", self.handle, _ptr(raw), B, Cc, Hc, Wc, grid, _ptr(out), self._s())
         return out
 
     def sample_descriptors(self, raw, grid, kp, kp_count, interp="bicubic"):
         raw, kp, kp_count = _dense(raw), _dense(kp), _dense(kp_count)
-        _chk_dev(raw, torch.float32, "desc_raw")
-        _chk_dev(kp, torch.int32, "kp")
-        _chk_dev(kp_count, torch.int32, "kp_count")
+        _chk_dev(raw, torch.float32, "desc_raw", self.device)
+        _chk_dev(kp, torch.int32, "kp", self.device)
+        _chk_dev(kp_count, torch.int32, "kp_count", self.device)
         B, Cc, Hc, Wc = raw.shape
         max_kp = kp.shape[1]
         out = torch.zeros((B, max_kp, Cc), dtype=torch.float32, device=raw.device)
         self._call("spn_sample_descriptors", self.handle, _ptr(raw), B, Cc, Hc, Wc, grid, _ptr(kp), _ptr(kp_count), max_kp,
-                   0 if interp == "bicubic" else 1, _ptr(out), _stream())
+                   0 if interp == "bicubic" else 1, _ptr(out), self._s())
         return out
 
     def box_nms(self, prob, size, iou=0.1, min_prob=0.01, top_k=0, det_thresh=None, want_map=True, want_pred=False,
                 max_kp=0):
         """prob (B,H,W).  Returns dict(nms, pred, kp, kp_count) with the requested members."""
         prob = _dense(prob)
-        _chk_dev(prob, torch.float32, "prob")
+        _chk_dev(prob, torch.float32, "prob", self.device)
         B, H, W = prob.shape
         dev = prob.device
         det = float(min_prob if det_thresh is None else det_thresh)
@@ -256,7 +263,7 @@ class Context:
                "kp_count": torch.zeros((B,), dtype=torch.int32, device=dev) if max_kp else None}
         self._call("spn_box_nms_topk", self.handle, _ptr(prob), B, H, W, C.c_float(size), C.c_float(iou), C.c_float(min_prob),
                    int(top_k), C.c_float(det), _ptr(out["nms"]), _ptr(out["pred"]), _ptr(out["kp"]), _ptr(out["kp_count"]),
-                   int(max_kp), _stream())
+                   int(max_kp), self._s())
         return out
 
     def nms_stats(self, B, H, W):
@@ -266,30 +273,32 @@ class Context:
 
     # ---- homography adaptation -------------------------------------------------------------------
     def warp_batch(self, images, hinv, margin, want_warped=True):
-        """images (NI,H,W), hinv (NI,n_h,3,3) -> warped (NI*(n_h+1),H,W) fp32 (None if not wanted), mask u8 (same shape)."""
+        """images (NI,H,W), hinv (NI,n_h,3,3) = kornia sampling matrices (``kornia_matrices`` / utils.kornia_geometry
+        ``fwd``) -> warped (NI*(n_h+1),H,W) fp32 (None if not wanted), mask u8 (same shape)."""
         images, hinv = _dense(images), _dense(hinv)
-        _chk_dev(images, torch.float32, "images")
+        _chk_dev(images, torch.float32, "images", self.device)
         NI, H, W = images.shape
         n_h = 0 if hinv is None else hinv.shape[1]
         if n_h:
-            _chk_dev(hinv, torch.float32, "hinv")
+            _chk_dev(hinv, torch.float32, "hinv", self.device)
         warped = torch.empty((NI * (n_h + 1), H, W), dtype=torch.float32, device=images.device) if want_warped else None
         mask = torch.empty((NI * (n_h + 1), H, W), dtype=torch.uint8, device=images.device)
         self._call("spn_warp_batch", self.handle, _ptr(images), NI, _ptr(hinv) if n_h else None, n_h, H, W, int(margin),
-                   _ptr(warped), _ptr(mask), _stream())
+                   _ptr(warped), _ptr(mask), self._s())
         return warped, mask
 
     def ha_aggregate(self, probs, h, margin, aggregation="sum"):
-        """probs (NI,n_h+1,H,W) masked heatmaps, h (NI,n_h,3,3) -> (NI,H,W)."""
+        """probs (NI,n_h+1,H,W) masked heatmaps, h (NI,n_h,3,3) = kornia sampling matrices of the inverse homographies
+        (``bwd``) -> (NI,H,W)."""
         probs, h = _dense(probs), _dense(h)
-        _chk_dev(probs, torch.float32, "probs")
+        _chk_dev(probs, torch.float32, "probs", self.device)
         NI, n1, H, W = probs.shape
         n_h = n1 - 1
         if n_h:
-            _chk_dev(h, torch.float32, "h")
+            _chk_dev(h, torch.float32, "h", self.device)
         out = torch.empty((NI, H, W), dtype=torch.float32, device=probs.device)
         self._call("spn_ha_aggregate", self.handle, _ptr(probs), _ptr(h) if n_h else None, NI, n_h, H, W, int(margin),
-                   1 if aggregation == "max" else 0, _ptr(out), _stream())
+                   1 if aggregation == "max" else 0, _ptr(out), self._s())
         return out
 
     def sample_homographies(self, params: dict, seed: int, first_index: int, count: int, H: int, W: int):
@@ -304,8 +313,17 @@ class Context:
         h = torch.empty((count, 3, 3), dtype=torch.float32, device=dev)
         hinv = torch.empty((count, 3, 3), dtype=torch.float32, device=dev)
         self._call("spn_sample_homographies", self.handle, C.byref(p), C.c_uint64(seed), C.c_uint64(first_index), count, H, W,
-                   _ptr(h), _ptr(hinv), _stream())
+                   _ptr(h), _ptr(hinv), self._s())
         return h, hinv
+
+    def kornia_matrices(self, h, H, W):
+        """h (...,3,3) fp32 CUDA pixel-space homographies -> (fwd, bwd) kornia sampling matrices, device arithmetic
+        (spn_kornia_matrices).  Host homographies: utils.kornia_geometry.sampling_matrices (the reference's bits)."""
+        h = _dense(h)
+        _chk_dev(h, torch.float32, "h", self.device)
+        fwd, bwd = torch.empty_like(h), torch.empty_like(h)
+        self._call("spn_kornia_matrices", self.handle, _ptr(h), h.numel() // 9, int(H), int(W), _ptr(fwd), _ptr(bwd), self._s())
+        return fwd, bwd
 
     def resize_crop(self, src: torch.Tensor, new_h, new_w, crop_top, crop_left, H, W, divisor=255.0):
         """src (H0,W0) uint8 or fp32 CUDA -> (H,W) fp32: bilinear resize + centre crop + /divisor (loader pre-processing)."""
@@ -314,14 +332,14 @@ class Context:
             raise NativeError("resize_crop: src must be a 2-D uint8/float32 CUDA tensor")
         out = torch.empty((H, W), dtype=torch.float32, device=src.device)
         self._call("spn_resize_crop", self.handle, _ptr(src), int(src.dtype == torch.uint8), src.shape[0], src.shape[1], int(new_h),
-                   int(new_w), int(crop_top), int(crop_left), int(H), int(W), C.c_float(divisor), _ptr(out), _stream())
+                   int(new_w), int(crop_top), int(crop_left), int(H), int(W), C.c_float(divisor), _ptr(out), self._s())
         return out
 
     def invert3x3(self, m):
         m = _dense(m)
-        _chk_dev(m, torch.float32, "m")
+        _chk_dev(m, torch.float32, "m", self.device)
         out = torch.empty_like(m)
-        self._call("spn_invert3x3", self.handle, _ptr(m), m.numel() // 9, _ptr(out), _stream())
+        self._call("spn_invert3x3", self.handle, _ptr(m), m.numel() // 9, _ptr(out), self._s())
         return out
 
 
@@ -332,7 +350,9 @@ def get_context(device=None) -> Context:
     """Process-wide context per GPU (weights are per-model: models create their own Context)."""
     if not torch.cuda.is_available():
         raise NativeError("CUDA is not available: superpoint-nerf-pytorch_b200 has no CPU fallback")
-    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    idx = None if device is None else torch.device(device).index
+    if idx is None:                      # 'cuda' without an index means torch's CURRENT device, not GPU 0
+        idx = torch.cuda.current_device()
     if idx not in _contexts:
         _contexts[idx] = Context(idx)
     return _contexts[idx]

@@ -172,7 +172,7 @@ sparse_desc_kernel(const float* __restrict__ raw, int C, int Hc, int Wc, int gri
 extern "C" int spn_dense_descriptors(spn_ctx* ctx, const float* d_desc_raw, int B, int C, int Hc, int Wc, int grid,
                                      float* d_desc, spn_stream stream) {
   SPN_REQUIRE(ctx && d_desc_raw && d_desc, "spn_dense_descriptors: null pointer");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   SPN_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hc > 0 && Wc > 0 && grid > 0, "spn_dense_descriptors: bad shape");
   const int H = Hc * grid, W = Wc * grid;
   SPN_REQUIRE(H <= 65535, "spn_dense_descriptors: image too tall");
@@ -192,7 +192,7 @@ extern "C" int spn_sample_descriptors(spn_ctx* ctx, const float* d_desc_raw, int
                                       const int32_t* d_kp, const int32_t* d_kp_count, int max_kp, int interp,
                                       float* d_out, spn_stream stream) {
   SPN_REQUIRE(ctx && d_desc_raw && d_kp && d_kp_count && d_out, "spn_sample_descriptors: null pointer");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   SPN_REQUIRE(B > 0 && B <= 65535 && C > 0 && Hc > 0 && Wc > 0 && grid > 0 && max_kp > 0, "spn_sample_descriptors: bad shape");
   SPN_REQUIRE(interp == 0 || interp == 1, "spn_sample_descriptors: interp must be 0 (bicubic) or 1 (bilinear)");
   dim3 g(spn_cdiv(max_kp, 8), B);

@@ -3,7 +3,10 @@
 //
 // Reference semantics (superpoint/superpoint/engine_solvers/export.py:42-114 and kornia 0.7.0 as restated in
 // oracle/kornia_shim.py): warp_perspective(src, M)(p) = interp(src, M^-1 p), align_corners=True, zeros padding,
-// nearest = round-half-even; erosion = min over the elliptical structuring element
+// nearest = round-half-even.  Source coordinates are evaluated with kornia's own normalised-space fp32 chain
+// (spn_geom.cuh: kornia_src) from the matrices Ainv = torch.inverse(normalize_homography(M)), so validity masks,
+// counts and bilinear samples are bit-identical to the reference's CPU run when Ainv is the reference's (the Python
+// binding computes it with the same torch calls); erosion = min over the elliptical structuring element
 // cv2.getStructuringElement(MORPH_ELLIPSE, (2m,2m)) with origin (m,m) and a geodesic border (pixels outside the
 // image never erode).
 //
@@ -62,7 +65,7 @@ ErodeK make_ellipse(int margin) {
 // Only tiles cut by the border of the warped quad need the per-pixel validity bits and the erosion.
 enum { kTileMixed = 0, kTileInside = 1, kTileOutside = 2, kTileDeep = 3 };
 
-__device__ __forceinline__ int classify_tile(const float* m, const ErodeK& ek, int tx0, int ty0, int H, int W,
+__device__ __forceinline__ int classify_tile(const float* a, const KGrid& g, const ErodeK& ek, int tx0, int ty0, int H, int W,
                                              bool want_deep = false) {
   // halo rectangle clipped to the image (out-of-image neighbours never erode: geodesic border)
   const int xa = max(tx0 - ek.org, 0), xb = min(tx0 + kTileW - 1 + (ek.ks - ek.org - 1), W - 1);
@@ -71,12 +74,10 @@ __device__ __forceinline__ int classify_tile(const float* m, const ErodeK& ek, i
   bool zok = true, in = true, deep = true, l = true, r = true, t = true, b = true;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const float x = (c & 1) ? (float)xb : (float)xa, y = (c & 2) ? (float)yb : (float)ya;
-    const float nx = fmaf(m[0], x, fmaf(m[1], y, m[2]));
-    const float ny = fmaf(m[3], x, fmaf(m[4], y, m[5]));
-    const float z = fmaf(m[6], x, fmaf(m[7], y, m[8]));
-    const float sc = 1.0f / (z + 1e-8f);
-    const float sx = nx * sc, sy = ny * sc;
+    const float xn = __ldg(&g.xs[(c & 1) ? xb : xa]), yn = __ldg(&g.ys[(c & 2) ? yb : ya]);
+    const float z = fmaf(a[6], xn, fmaf(a[7], yn, a[8]));
+    float sx, sy;
+    kornia_src(a, xn, yn, g.hw, g.hh, sx, sy);
     zok = zok && z > 1e-3f;
     in = in && sx >= -0.5f + mg && sx <= (float)W - 0.5f - mg && sy >= -0.5f + mg && sy <= (float)H - 0.5f - mg;
     deep = deep && sx >= mg && sx <= (float)W - 1.0f - mg && sy >= mg && sy <= (float)H - 1.0f - mg;
@@ -95,8 +96,8 @@ __device__ __forceinline__ int classify_tile(const float* m, const ErodeK& ek, i
 // per 32 positions; positions outside the image count as valid (geodesic border).
 constexpr int kRawWords = (kRawH * kRawW + 31) / 32 + 1;
 
-__device__ __forceinline__ void fill_raw_bits(uint32_t* bits, const float* m, const ErodeK& ek, int tx0, int ty0, int H,
-                                              int W) {
+__device__ __forceinline__ void fill_raw_bits(uint32_t* bits, const float* a, const KGrid& g, const ErodeK& ek, int tx0,
+                                              int ty0, int H, int W) {
   const int rh = kTileH + ek.ks - 1, rw = kTileW + ek.ks - 1;
   const int n = rh * rw;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -109,7 +110,7 @@ __device__ __forceinline__ void fill_raw_bits(uint32_t* bits, const float* m, co
       v = 1;
       if (x >= 0 && x < W && y >= 0 && y < H) {
         float sx, sy;
-        apply_h(m, (float)x, (float)y, sx, sy);
+        kornia_src(a, __ldg(&g.xs[x]), __ldg(&g.ys[y]), g.hw, g.hh, sx, sy);
         v = inside_nearest(sx, sy, H, W);
       }
     }
@@ -139,7 +140,7 @@ __device__ __forceinline__ int eroded_bits(const uint32_t* bits, const uint32_t*
 constexpr int kMaxRowTiles = 256;
 
 __global__ void __launch_bounds__(256)
-warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hinv, int n_h, int H, int W,
+warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ ainv, KGrid g, int n_h, int H, int W,
                   int tiles_x, ErodeK ek, float* __restrict__ warped, uint8_t* __restrict__ mask) {
   __shared__ uint32_t bits[2][kRawWords];
   __shared__ float m[9];
@@ -160,10 +161,11 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hi
       }
     return;
   }
-  if (threadIdx.x < 9) m[threadIdx.x] = __ldg(&hinv[((size_t)img * n_h + (j - 1)) * 9 + threadIdx.x]);
+  if (threadIdx.x < 9) m[threadIdx.x] = __ldg(&ainv[((size_t)img * n_h + (j - 1)) * 9 + threadIdx.x]);
   if (threadIdx.x >= 32 && threadIdx.x < 32 + kMaxKs) rows_s[threadIdx.x - 32] = ek.rows[threadIdx.x - 32];
   __syncthreads();
-  for (int t = threadIdx.x; t < tiles_x; t += blockDim.x) cls_s[t] = (uint8_t)classify_tile(m, ek, t * kTileW, ty0, H, W);
+  for (int t = threadIdx.x; t < tiles_x; t += blockDim.x) cls_s[t] = (uint8_t)classify_tile(m, g, ek, t * kTileW, ty0, H, W);
+  const float yn = y < H ? __ldg(&g.ys[y]) : 0.f;
   __syncthreads();
   int nmixed = 0;
   for (int t = 0; t < tiles_x; ++t) {
@@ -181,15 +183,15 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ hi
     if (cls == kTileMixed) {
       uint32_t* bb = bits[nmixed & 1];
       ++nmixed;
-      fill_raw_bits(bb, m, ek, tx0, ty0, H, W);
+      fill_raw_bits(bb, m, g, ek, tx0, ty0, H, W);
       __syncthreads();
       mk = eroded_bits(bb, rows_s, ek.ks, tx, ty);
     }
     if (in_img) {
       if (warped) {  // null: mask only (the fused encoder warps on the fly)
         float sx, sy;
-        apply_h(m, (float)x, (float)y, sx, sy);
-        warped[orow + x] = bilinear_zero(src, sx, sy, H, W);
+        kornia_src(m, __ldg(&g.xs[x]), yn, g.hw, g.hh, sx, sy);
+        warped[orow + x] = bilinear_zero_exact(src, sx, sy, H, W);
       }
       mask[orow + x] = (uint8_t)mk;
     }
@@ -202,14 +204,16 @@ struct DeepTaps {
 
 // Issue the four loads of one bilinear sample whose taps are all inside the image (tile class "deep").
 __device__ __forceinline__ DeepTaps deep_taps(const float* __restrict__ pimg, const float4* __restrict__ hs4,
-                                              const float* __restrict__ hs, int j, int hw, int W, float fx, float fy) {
+                                              const float* __restrict__ hs, int j, int hw, int W, float xn, float yn,
+                                              float ghw, float ghh) {
   const float4 r0 = hs4[j * 3], r1 = hs4[j * 3 + 1];
   const float m8 = hs[j * 12 + 8];
-  const float nx = fmaf(r0.x, fx, fmaf(r0.y, fy, r0.z));
-  const float ny = fmaf(r0.w, fx, fmaf(r1.x, fy, r1.y));
-  const float z = fmaf(r1.z, fx, fmaf(r1.w, fy, m8));
-  const float sc = rcp_normal(z + 1e-8f);
-  const float sx = nx * sc, sy = ny * sc;
+  // kornia_src on the rows held in registers (tile class "deep" guarantees z > 1e-3: the |z| > 1e-8 select is moot)
+  const float qx = __fadd_rn(fmaf(r0.y, yn, __fmul_rn(r0.x, xn)), r0.z);
+  const float qy = __fadd_rn(fmaf(r1.x, yn, __fmul_rn(r0.w, xn)), r1.y);
+  const float qz = __fadd_rn(fmaf(r1.w, yn, __fmul_rn(r1.z, xn)), m8);
+  const float sc = rcp_normal(__fadd_rn(qz, 1e-8f));
+  const float sx = __fmul_rn(__fadd_rn(__fmul_rn(sc, qx), 1.0f), ghw), sy = __fmul_rn(__fadd_rn(__fmul_rn(sc, qy), 1.0f), ghh);
   const float flx = floorf(sx), fly = floorf(sy);
   const float* p = pimg + ((j + 1) * hw + (int)fly * W + (int)flx);
   DeepTaps t;
@@ -217,21 +221,23 @@ __device__ __forceinline__ DeepTaps deep_taps(const float* __restrict__ pimg, co
   t.v01 = __ldg(p + 1);
   t.v10 = __ldg(p + W);
   t.v11 = __ldg(p + W + 1);
-  t.ax = sx - flx;
-  t.ay = sy - fly;
+  t.ax = __fsub_rn(sx, flx);
+  t.ay = __fsub_rn(sy, fly);
   return t;
 }
 
+// ATen's CPU bilinear arithmetic (spn_geom.cuh: bilinear_combine) on taps already in registers
 __device__ __forceinline__ float deep_value(const DeepTaps& t) {
-  const float top = fmaf(t.ax, t.v01 - t.v00, t.v00), bot = fmaf(t.ax, t.v11 - t.v10, t.v10);
-  return fmaf(t.ay, bot - top, top);
+  const float e = __fsub_rn(1.0f, t.ax), s = __fsub_rn(1.0f, t.ay);
+  return fmaf(t.v11, __fmul_rn(t.ay, t.ax),
+              fmaf(t.v10, __fmul_rn(t.ay, e), fmaf(t.v01, __fmul_rn(s, t.ax), __fmul_rn(t.v00, __fmul_rn(s, e)))));
 }
 
 // One block per 32 x 8 output tile of one image.  The homographies are first classified for this tile; the "deep"
 // ones (most of them: whole tile valid, all taps in bounds) run as a barrier-free loop with two samples in flight per
 // thread; the tiles cut by a warped border go through the validity bits + erosion.
 __global__ void __launch_bounds__(256, 4)
-ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ hmat, int n_h, int H, int W,
+ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ hmat, KGrid g, int n_h, int H, int W,
                     int tiles_x, ErodeK ek, int agg_max, float* __restrict__ out) {
   extern __shared__ float4 hs4[];  // n_h homographies padded to 12 floats, then three byte arrays of n_h entries
   __shared__ uint32_t bits[2][kRawWords];
@@ -245,8 +251,8 @@ ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ h
   const int tx0 = (blockIdx.x % tiles_x) * kTileW, ty0 = (blockIdx.x / tiles_x) * kTileH;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int x = tx0 + tx, y = ty0 + ty;
-  const float fx = (float)x, fy = (float)y;
   const bool in_img = x < W && y < H;
+  const float xn = in_img ? __ldg(&g.xs[x]) : 0.f, yn = in_img ? __ldg(&g.ys[y]) : 0.f;
   for (int i = threadIdx.x; i < n_h * 9; i += blockDim.x) hs[(i / 9) * 12 + i % 9] = __ldg(&hmat[(size_t)img * n_h * 9 + i]);
   if (threadIdx.x < kMaxKs) rows_s[threadIdx.x] = ek.rows[threadIdx.x];
   const float* pimg = probs + (size_t)img * (n_h + 1) * H * W;
@@ -258,7 +264,7 @@ ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ h
   }
   __syncthreads();
   for (int j = threadIdx.x; j < n_h; j += blockDim.x)
-    cls_s[j] = (uint8_t)classify_tile(hs + j * 12, ek, tx0, ty0, H, W, true);
+    cls_s[j] = (uint8_t)classify_tile(hs + j * 12, g, ek, tx0, ty0, H, W, true);
   __syncthreads();
   if (threadIdx.x < 32) {  // ordered compaction into the two work lists (outside tiles contribute nothing: dropped)
     int nd = 0, nr = 0;
@@ -283,10 +289,10 @@ ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ h
   if (in_img) {
     int k = 0;
     for (; k + 3 < n_deep; k += 4) {  // four samples (16 loads) in flight per thread
-      const DeepTaps a = deep_taps(pimg, hs4, hs, deep_s[k], hw, W, fx, fy);
-      const DeepTaps b = deep_taps(pimg, hs4, hs, deep_s[k + 1], hw, W, fx, fy);
-      const DeepTaps c = deep_taps(pimg, hs4, hs, deep_s[k + 2], hw, W, fx, fy);
-      const DeepTaps d = deep_taps(pimg, hs4, hs, deep_s[k + 3], hw, W, fx, fy);
+      const DeepTaps a = deep_taps(pimg, hs4, hs, deep_s[k], hw, W, xn, yn, g.hw, g.hh);
+      const DeepTaps b = deep_taps(pimg, hs4, hs, deep_s[k + 1], hw, W, xn, yn, g.hw, g.hh);
+      const DeepTaps c = deep_taps(pimg, hs4, hs, deep_s[k + 2], hw, W, xn, yn, g.hw, g.hh);
+      const DeepTaps d = deep_taps(pimg, hs4, hs, deep_s[k + 3], hw, W, xn, yn, g.hw, g.hh);
       const float va = deep_value(a), vb = deep_value(b), vc = deep_value(c), vd = deep_value(d);
       acc += va;
       acc += vb;
@@ -295,7 +301,7 @@ ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ h
       mx = fmaxf(fmaxf(mx, fmaxf(va, vb)), fmaxf(vc, vd));
     }
     for (; k < n_deep; ++k) {
-      const float va = deep_value(deep_taps(pimg, hs4, hs, deep_s[k], hw, W, fx, fy));
+      const float va = deep_value(deep_taps(pimg, hs4, hs, deep_s[k], hw, W, xn, yn, g.hw, g.hh));
       acc += va;
       mx = fmaxf(mx, va);
     }
@@ -309,14 +315,14 @@ ha_aggregate_kernel(const float* __restrict__ probs, const float* __restrict__ h
     if (cls_s[j] == kTileMixed) {        // block-uniform
       uint32_t* bb = bits[nmixed & 1];   // double buffered: one barrier per mixed homography
       ++nmixed;
-      fill_raw_bits(bb, m, ek, tx0, ty0, H, W);
+      fill_raw_bits(bb, m, g, ek, tx0, ty0, H, W);
       __syncthreads();
       c = eroded_bits(bb, rows_s, ek.ks, tx, ty);
     }
     if (in_img && c) {
       float sx, sy;
-      apply_h(m, fx, fy, sx, sy);
-      const float v = bilinear_zero(pimg + (j + 1) * hw, sx, sy, H, W);
+      kornia_src(m, xn, yn, g.hw, g.hh, sx, sy);
+      const float v = bilinear_zero_exact(pimg + (j + 1) * hw, sx, sy, H, W);
       acc += v;
       cnt += 1.f;
       mx = fmaxf(mx, v);
@@ -484,6 +490,38 @@ __global__ void invert3x3_kernel(const float* __restrict__ in, int count, float*
   for (int k = 0; k < 9; ++k) out[(size_t)i * 9 + k] = o[k];
 }
 
+// kornia normalize_homography + inverse for a batch of pixel-space homographies (the matrices K.warp_perspective
+// builds internally at export.py:51-55,72): fwd = inverse(N (M N^-1)) samples the source of warp(., M);
+// bwd = the same for M^-1 (export.py:49).  N = normal_transform_pixel(H, W); products in the reference's order (no
+// FMA); the 3x3 inverses use the adjugate, which agrees with the reference's LAPACK inverse to a few ulp, not bit for
+// bit (for bit-exact masks the caller passes matrices computed with the reference's own torch.inverse).
+__device__ void mm3_ref(const float* A, const float* B, float* C) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      C[i * 3 + j] = __fadd_rn(__fadd_rn(__fmul_rn(A[i * 3], B[j]), __fmul_rn(A[i * 3 + 1], B[3 + j])), __fmul_rn(A[i * 3 + 2], B[6 + j]));
+}
+
+__global__ void kornia_matrices_kernel(const float* __restrict__ h, int count, int H, int W, float* __restrict__ fwd,
+                                       float* __restrict__ bwd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float ax = __fdiv_rn(2.0f, (float)(W - 1)), ay = __fdiv_rn(2.0f, (float)(H - 1));
+  const float n[9] = {ax, 0.f, -1.f, 0.f, ay, -1.f, 0.f, 0.f, 1.f};
+  const float rx = __frcp_rn(ax), ry = __frcp_rn(ay);
+  const float ni[9] = {rx, 0.f, rx, 0.f, ry, ry, 0.f, 0.f, 1.f};
+  float m[9], mi[9], t[9], a[9], o[9];
+  for (int k = 0; k < 9; ++k) m[k] = h[(size_t)i * 9 + k];
+  inv3x3(m, mi);
+  mm3_ref(m, ni, t);
+  mm3_ref(n, t, a);
+  inv3x3(a, o);
+  for (int k = 0; k < 9; ++k) fwd[(size_t)i * 9 + k] = o[k];
+  mm3_ref(mi, ni, t);
+  mm3_ref(n, t, a);
+  inv3x3(a, o);
+  for (int k = 0; k < 9; ++k) bwd[(size_t)i * 9 + k] = o[k];
+}
+
 // Loader pre-processing (data/COCO.py:66-76, data/HPatches.py:64-72): bilinear resize (align_corners=False, no
 // antialias, i.e. F.interpolate as kornia.resize calls it) + centre crop (zero pad if the resized image is smaller)
 // + division by 255, fused; source is the decoded grayscale image as uint8 or float32.
@@ -513,7 +551,7 @@ resize_crop_kernel(const T* __restrict__ src, int H0, int W0, int nh, int nw, in
 extern "C" int spn_resize_crop(spn_ctx* ctx, const void* d_src, int src_is_u8, int H0, int W0, int new_h, int new_w,
                                int crop_top, int crop_left, int H, int W, float divisor, float* d_out, spn_stream stream) {
   SPN_REQUIRE(ctx && d_src && d_out, "spn_resize_crop: null pointer");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   SPN_REQUIRE(H0 > 0 && W0 > 0 && new_h > 0 && new_w > 0 && H > 0 && W > 0 && divisor != 0.f, "spn_resize_crop: bad shape");
   dim3 grid(spn_cdiv(W, 32), spn_cdiv(H, 8));
   if (src_is_u8)
@@ -526,12 +564,58 @@ extern "C" int spn_resize_crop(spn_ctx* ctx, const void* d_src, int src_is_u8, i
   return SPN_OK;
 }
 
-extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h, int H,
+// kornia create_meshgrid coordinates, tabulated per image size: xs[i] = (i / (W-1) - 0.5) * 2 in IEEE fp32, the
+// reference's operation order (linspace(0, W-1, W) is exact integers).  Cached per (H, W) in the context.
+static int kornia_grid(spn_ctx* ctx, int H, int W, cudaStream_t s, KGrid* out) {
+  SPN_REQUIRE(H >= 2 && W >= 2, "kornia grid needs H, W >= 2");
+  for (auto& e : ctx->grids)
+    if (e.H == H && e.W == W) {
+      *out = KGrid{e.tab, e.tab + W, 0.5f * (float)(W - 1), 0.5f * (float)(H - 1)};
+      return SPN_OK;
+    }
+  std::vector<float> host((size_t)W + H);
+  for (int i = 0; i < W; ++i) {
+    volatile float q = (float)i / (float)(W - 1);
+    volatile float d = q - 0.5f;
+    host[i] = d * 2.0f;
+  }
+  for (int i = 0; i < H; ++i) {
+    volatile float q = (float)i / (float)(H - 1);
+    volatile float d = q - 0.5f;
+    host[W + i] = d * 2.0f;
+  }
+  SpnGridTab e;
+  e.H = H; e.W = W; e.tab = nullptr;
+  SPN_CUDA(cudaMalloc((void**)&e.tab, host.size() * sizeof(float)));
+  // pageable source: the copy is staged before the call returns, so `host` may go out of scope
+  SPN_CUDA(cudaMemcpyAsync(e.tab, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  ctx->grids.push_back(e);
+  *out = KGrid{e.tab, e.tab + W, 0.5f * (float)(W - 1), 0.5f * (float)(H - 1)};
+  return SPN_OK;
+}
+
+extern "C" int spn_kornia_matrices(spn_ctx* ctx, const float* d_h, int count, int H, int W, float* d_ainv_fwd,
+                                   float* d_ainv_bwd, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_h && d_ainv_fwd && d_ainv_bwd && count >= 0, "spn_kornia_matrices: bad argument");
+  SPN_REQUIRE(H >= 2 && W >= 2, "spn_kornia_matrices: H, W must be >= 2");
+  SpnDeviceGuard guard(ctx->device);
+  if (count == 0) return SPN_OK;
+  kornia_matrices_kernel<<<spn_cdiv(count, 128), 128, 0, (cudaStream_t)stream>>>(d_h, count, H, W, d_ainv_fwd, d_ainv_bwd);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}
+
+extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_ainv, int n_h, int H,
                               int W, int margin, float* d_warped, uint8_t* d_mask, spn_stream stream) {
   SPN_REQUIRE(ctx && d_images && d_mask, "spn_warp_batch: null pointer");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   SPN_REQUIRE(n_images > 0 && n_h >= 0 && H > 0 && W > 0, "spn_warp_batch: bad shape");
-  SPN_REQUIRE(n_h == 0 || d_hinv, "spn_warp_batch: d_hinv is null");
+  SPN_REQUIRE(n_h == 0 || d_ainv, "spn_warp_batch: d_ainv is null");
+  KGrid kg;
+  {
+    const int rc = kornia_grid(ctx, H, W, (cudaStream_t)stream, &kg);
+    if (rc) return rc;
+  }
   // the reference's valid_border_margin == 0 path is shape-broken: unsupported
   SPN_REQUIRE(margin >= 1 && 2 * margin <= kMaxKs, "spn_warp_batch: valid_border_margin must be in [1,%d]", kMaxKs / 2);
   SPN_REQUIRE((size_t)n_images * (n_h + 1) <= 65535, "spn_warp_batch: too many slots per launch");
@@ -540,7 +624,7 @@ extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images,
   SPN_REQUIRE(tiles_x <= kMaxRowTiles, "spn_warp_batch: W must be <= %d", kMaxRowTiles * kTileW);
   dim3 grid(tiles_y, n_images * (n_h + 1));
   SpnProfScope prof(ctx, SPN_PROF_WARP, (cudaStream_t)stream);
-  warp_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_images, d_hinv, n_h, H, W, tiles_x, ek, d_warped, d_mask);
+  warp_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_images, d_ainv, kg, n_h, H, W, tiles_x, ek, d_warped, d_mask);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }
@@ -548,7 +632,12 @@ extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images,
 extern "C" int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float* d_h, int n_images, int n_h, int H,
                                 int W, int margin, int aggregation, float* d_out, spn_stream stream) {
   SPN_REQUIRE(ctx && d_probs && d_out, "spn_ha_aggregate: null pointer");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
+  KGrid kg;
+  {
+    const int rc = kornia_grid(ctx, H, W, (cudaStream_t)stream, &kg);
+    if (rc) return rc;
+  }
   SPN_REQUIRE(n_images > 0 && n_images <= 65535 && n_h >= 0 && H > 0 && W > 0, "spn_ha_aggregate: bad shape");
   SPN_REQUIRE(n_h == 0 || d_h, "spn_ha_aggregate: d_h is null");
   SPN_REQUIRE(margin >= 1 && 2 * margin <= kMaxKs, "spn_ha_aggregate: valid_border_margin must be in [1,%d]", kMaxKs / 2);
@@ -559,7 +648,7 @@ extern "C" int spn_ha_aggregate(spn_ctx* ctx, const float* d_probs, const float*
   const int tiles_x = spn_cdiv(W, kTileW), tiles_y = spn_cdiv(H, kTileH);
   dim3 grid(tiles_x * tiles_y, n_images);
   SpnProfScope prof(ctx, SPN_PROF_AGGREGATE, (cudaStream_t)stream);
-  ha_aggregate_kernel<<<grid, 256, n_h * 12 * sizeof(float) + 3 * ((n_h + 15) & ~15), (cudaStream_t)stream>>>(d_probs, d_h, n_h, H, W, tiles_x, ek,
+  ha_aggregate_kernel<<<grid, 256, n_h * 12 * sizeof(float) + 3 * ((n_h + 15) & ~15), (cudaStream_t)stream>>>(d_probs, d_h, kg, n_h, H, W, tiles_x, ek,
                                                                                      aggregation, d_out);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
@@ -569,7 +658,7 @@ extern "C" int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params
                                        uint64_t first_index, int count, int H, int W, float* d_h, float* d_hinv,
                                        spn_stream stream) {
   SPN_REQUIRE(ctx && params && d_h && d_hinv, "spn_sample_homographies: null pointer");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   SPN_REQUIRE(count >= 0 && H > 0 && W > 0, "spn_sample_homographies: bad shape");
   SPN_REQUIRE(params->n_scales >= 1 && params->n_scales <= 31 && params->n_angles >= 1 && params->n_angles <= 63,
               "spn_sample_homographies: n_scales must be in [1,31], n_angles in [1,63]");
@@ -583,7 +672,7 @@ extern "C" int spn_sample_homographies(spn_ctx* ctx, const spn_homography_params
 
 extern "C" int spn_invert3x3(spn_ctx* ctx, const float* d_in, int count, float* d_out, spn_stream stream) {
   SPN_REQUIRE(ctx && d_in && d_out && count >= 0, "spn_invert3x3: bad argument");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   if (count == 0) return SPN_OK;
   invert3x3_kernel<<<spn_cdiv(count, 128), 128, 0, (cudaStream_t)stream>>>(d_in, count, d_out);
   SPN_CHECK_LAUNCH(ctx);

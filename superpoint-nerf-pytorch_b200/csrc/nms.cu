@@ -474,7 +474,7 @@ nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ st
 
 extern "C" int spn_nms_stats(spn_ctx* ctx, int B, int H, int W, int64_t* h_out) {
   SPN_REQUIRE(ctx && h_out && ctx->aux, "spn_nms_stats: nothing to read");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   const size_t status_bytes = ((size_t)B * H * W + 255) & ~(size_t)255;
   unsigned v[8];
   SPN_CUDA(cudaDeviceSynchronize());
@@ -487,7 +487,7 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
                                 float min_prob, int top_k, float det_thresh, float* d_nms, int32_t* d_pred,
                                 int32_t* d_kp, int32_t* d_kp_count, int max_kp, spn_stream stream) {
   SPN_REQUIRE(ctx && d_prob, "spn_box_nms_topk: null pointer");
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   SPN_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "spn_box_nms_topk: bad shape");
   SPN_REQUIRE(size > 0.f && size <= 8.f, "spn_box_nms_topk: box size must be in (0, 8]");
   SPN_REQUIRE(!d_kp || max_kp > 0, "spn_box_nms_topk: max_kp must be > 0 when d_kp is given");
@@ -505,7 +505,6 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
   foot.r = 0;
   for (int k = 0; k < foot.n; ++k) foot.r = max(foot.r, max(abs((int)foot.dy[k]), abs((int)foot.dx[k])));
   cudaStream_t s = (cudaStream_t)stream;
-  SPN_CUDA(cudaSetDevice(ctx->device));
   const size_t status_bytes = ((size_t)B * H * W + 255) & ~(size_t)255;
   int tiles_x = spn_cdiv(W, 32), tiles_y = spn_cdiv(H, 32);
   const long long n_tiles = (long long)B * tiles_x * tiles_y;

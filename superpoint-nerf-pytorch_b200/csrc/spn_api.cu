@@ -51,7 +51,7 @@ extern "C" int spn_create(spn_ctx** out, int device) {
     return SPN_E_CUDA;
   }
   SPN_REQUIRE(device >= 0 && device < n, "spn_create: device %d out of range [0,%d)", device, n);
-  SPN_CUDA(cudaSetDevice(device));
+  SpnDeviceGuard guard(device);
   cudaDeviceProp prop;
   SPN_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
@@ -67,9 +67,10 @@ extern "C" int spn_create(spn_ctx** out, int device) {
 
 extern "C" int spn_destroy(spn_ctx* ctx) {
   if (!ctx) return SPN_OK;
-  cudaSetDevice(ctx->device);
+  SpnDeviceGuard guard(ctx->device);
   cudaDeviceSynchronize();
   spn_tc_destroy(ctx);
+  for (auto& g : ctx->grids) cudaFree(g.tab);
   for (auto& L : ctx->layers) {
     if (L.w32) cudaFree(L.w32);
     if (L.bias) cudaFree(L.bias);
@@ -112,7 +113,7 @@ extern "C" int spn_pack_weights(spn_ctx* ctx, int layer, const float* h_w, const
   SPN_REQUIRE(layer >= 0 && layer < SPN_NUM_LAYERS, "spn_pack_weights: layer %d out of range", layer);
   SPN_REQUIRE((ksize == 1 || ksize == 3) && cin > 0 && cout > 0, "spn_pack_weights: unsupported conv %dx%d %d->%d", ksize, ksize, cin, cout);
   cudaStream_t s = (cudaStream_t)stream;
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   const int taps = ksize * ksize;
   const int cout_pad = (cout + 15) / 16 * 16;
   // fold eval-mode BatchNorm (VGG_Backbone.py:28-29): y = (conv + b - mean) * gamma / sqrt(var + eps) + beta
@@ -173,7 +174,7 @@ extern "C" int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, i
   int rc = check_image_shape(B, H, W);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   for (int l = SPN_L_BLOCK1; l <= SPN_L_BLOCK8; ++l)
     if (!ctx->layers[l].w32) { spn_set_error("spn_encoder_forward: layer %d has no weights", l); return SPN_E_STATE; }
   if (mode == SPN_MODE_F16 || mode == SPN_MODE_BF16) {
@@ -213,7 +214,7 @@ extern "C" int spn_encoder_forward_ha(spn_ctx* ctx, const float* d_images, int n
   SPN_REQUIRE(mode == SPN_MODE_F16 || mode == SPN_MODE_BF16,
               "spn_encoder_forward_ha: the fused warp+encoder exists for the tensor-core modes only (fp32: spn_warp_batch + spn_encoder_forward)");
   cudaStream_t s = (cudaStream_t)stream;
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   for (int l = SPN_L_BLOCK1; l <= SPN_L_BLOCK8; ++l)
     if (!ctx->layers[l].w32) { spn_set_error("spn_encoder_forward_ha: layer %d has no weights", l); return SPN_E_STATE; }
   // n_h == 0 still goes through the slot path (slot == image)
@@ -237,7 +238,7 @@ extern "C" int spn_detector_head_forward(spn_ctx* ctx, int B, int H, int W, int 
   int rc = check_feat(ctx, B, H, W, mode, "spn_detector_head_forward");
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   const SpnLayer& Pb = ctx->layers[SPN_L_CONVPB];
   if (!ctx->layers[SPN_L_CONVPA].w32 || !Pb.w32) { spn_set_error("detector head has no weights"); return SPN_E_STATE; }
   SPN_REQUIRE(Pb.cout == 65, "detector head must have 65 output channels (grid_size 8), got %d", Pb.cout);
@@ -265,7 +266,7 @@ extern "C" int spn_descriptor_head_forward(spn_ctx* ctx, int B, int H, int W, in
   int rc = check_feat(ctx, B, H, W, mode, "spn_descriptor_head_forward");
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   if (!ctx->layers[SPN_L_CONVDA].w32 || !ctx->layers[SPN_L_CONVDB].w32) {
     spn_set_error("descriptor head has no weights (model_name != 'superpoint'?)");
     return SPN_E_STATE;
@@ -286,7 +287,7 @@ extern "C" int spn_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_
   SPN_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, "spn_conv_layer: bad shape");
   SPN_REQUIRE(!pool || (H % 2 == 0 && W % 2 == 0 && ctx->layers[layer].ks == 3), "spn_conv_layer: pooling needs even H, W and a 3x3 layer");
   cudaStream_t s = (cudaStream_t)stream;
-  SPN_CUDA(cudaSetDevice(ctx->device));
+  SpnDeviceGuard guard(ctx->device);
   ctx->feat_mode = -1;  // the workspace is reused
   if (mode == SPN_MODE_FP32 || ctx->layers[layer].cin % 64 != 0) return spn_conv_fp32(ctx, layer, d_in, d_out, B, H, W, relu != 0, pool != 0, s);
   SPN_REQUIRE(mode == SPN_MODE_F16 || mode == SPN_MODE_BF16, "spn_conv_layer: unknown mode %d", mode);

@@ -24,8 +24,27 @@ struct SpnProfRec {
   cudaEvent_t a, b;
 };
 
+struct SpnGridTab {  // kornia create_meshgrid coordinates of one image size: xs[W] then ys[H] (geometry.cu)
+  int H, W;
+  float* tab;
+};
+
+// Makes the context's GPU current for the duration of an entry point and restores the caller's device afterwards
+// (PyTorch's current device must not change behind its back).
+struct SpnDeviceGuard {
+  int prev = -1;
+  explicit SpnDeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~SpnDeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 struct spn_ctx {
   bool prof_on = false;
+  std::vector<SpnGridTab> grids;
   std::vector<SpnProfRec> prof;
   int device = 0;
   int sm_count = 148;

@@ -80,6 +80,71 @@ __device__ __forceinline__ float bilinear_zero_nb(const float* __restrict__ img,
   return v;
 }
 
+// ---- kornia 0.7.0 warp_perspective coordinate chain, bit for bit (oracle/kornia_shim.py; the arithmetic below was
+// fitted against torch-CPU fp32 on the same matrices: tools/kornia_chain_fit.py) -------------------------------------
+//   xn = (x / (W-1) - 0.5) * 2, yn likewise                      (create_meshgrid; tabulated on the host, KGrid)
+//   q  = [xn, yn, 1] @ Ainv^T  as  (a0*xn  ->  fma(a1, yn, .)  ->  + a2)   (torch.bmm, K = 3)
+//   g  = q.xy * (|q.z| > 1e-8 ? 1 / (q.z + 1e-8) : 1)              (transform_points)
+//   s  = (g + 1) * (size-1)/2                                      (grid_sample unnormalize, align_corners=True)
+// `a` = torch.inverse(normalize_homography(M)) in normalised coordinates.  Every operation is a single IEEE fp32
+// operation in the reference's order (intrinsics keep the compiler from contracting or re-associating them).
+struct KGrid {
+  const float* xs;  // [W] normalised x of every column
+  const float* ys;  // [H]
+  float hw, hh;     // (W-1)/2, (H-1)/2
+};
+
+__device__ __forceinline__ void kornia_src(const float* __restrict__ a, float xn, float yn, float hw, float hh, float& sx,
+                                           float& sy) {
+  const float qx = __fadd_rn(fmaf(a[1], yn, __fmul_rn(a[0], xn)), a[2]);
+  const float qy = __fadd_rn(fmaf(a[4], yn, __fmul_rn(a[3], xn)), a[5]);
+  const float qz = __fadd_rn(fmaf(a[7], yn, __fmul_rn(a[6], xn)), a[8]);
+  const float sc = fabsf(qz) > 1e-8f ? __frcp_rn(__fadd_rn(qz, 1e-8f)) : 1.0f;
+  sx = __fmul_rn(__fadd_rn(__fmul_rn(sc, qx), 1.0f), hw);
+  sy = __fmul_rn(__fadd_rn(__fmul_rn(sc, qy), 1.0f), hh);
+}
+
+// F.grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True) of one channel with ATen's CPU arithmetic:
+// w = x - floor(x), e = 1 - w, n = y - floor(y), s = 1 - n; weights s*e, s*w, n*e, n*w; taps outside the image read 0;
+// value = fma(se_v, se, fma(sw_v, sw, fma(ne_v, ne, nw_v * nw))).
+__device__ __forceinline__ float bilinear_combine(float nwv, float nev, float swv, float sev, float sx, float sy, float fx,
+                                                  float fy) {
+  const float w = __fsub_rn(sx, fx), e = __fsub_rn(1.0f, w), n = __fsub_rn(sy, fy), s = __fsub_rn(1.0f, n);
+  const float nw = __fmul_rn(s, e), ne = __fmul_rn(s, w), sw = __fmul_rn(n, e), se = __fmul_rn(n, w);
+  return fmaf(sev, se, fmaf(swv, sw, fmaf(nev, ne, __fmul_rn(nwv, nw))));
+}
+
+__device__ __forceinline__ float bilinear_zero_exact(const float* __restrict__ img, float sx, float sy, int H, int W) {
+  if (!(sx > -1.f && sx < (float)W && sy > -1.f && sy < (float)H)) return 0.f;  // every tap outside (also NaN/inf)
+  const float fx = floorf(sx), fy = floorf(sy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const bool xin0 = x0 >= 0, xin1 = x0 + 1 < W, yin0 = y0 >= 0, yin1 = y0 + 1 < H;
+  const float nwv = (yin0 && xin0) ? __ldg(&img[(size_t)y0 * W + x0]) : 0.f;
+  const float nev = (yin0 && xin1) ? __ldg(&img[(size_t)y0 * W + x0 + 1]) : 0.f;
+  const float swv = (yin1 && xin0) ? __ldg(&img[(size_t)(y0 + 1) * W + x0]) : 0.f;
+  const float sev = (yin1 && xin1) ? __ldg(&img[(size_t)(y0 + 1) * W + x0 + 1]) : 0.f;
+  return bilinear_combine(nwv, nev, swv, sev, sx, sy, fx, fy);
+}
+
+// Pixel-space matrix equivalent to a normalised kornia sampling matrix (for the fused 16-bit front end, where the
+// last bits of the coordinate do not matter): p_src = m . (x, y, 1) up to the homogeneous divide.
+__device__ __forceinline__ void kornia_to_pixel(const float* __restrict__ a, int H, int W, float* __restrict__ m) {
+  const double sxn = 2.0 / (double)(W - 1), syn = 2.0 / (double)(H - 1), hw = 0.5 * (W - 1), hh = 0.5 * (H - 1);
+  double r[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r[k][0] = (double)a[3 * k] * sxn;
+    r[k][1] = (double)a[3 * k + 1] * syn;
+    r[k][2] = (double)a[3 * k + 2] - (double)a[3 * k] - (double)a[3 * k + 1];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    m[c] = (float)(hw * (r[0][c] + r[2][c]));
+    m[3 + c] = (float)(hh * (r[1][c] + r[2][c]));
+    m[6 + c] = (float)r[2][c];
+  }
+}
+
 // Exact t / d for 0 <= t, t * d < 2^40, with m = ceil(2^40 / d) computed on the host (fast_div_magic).
 __device__ __forceinline__ int fast_div(int t, unsigned long long m) {
   return (int)(((unsigned long long)(unsigned)t * m) >> 40);

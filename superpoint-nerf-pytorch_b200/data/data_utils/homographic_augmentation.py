@@ -85,6 +85,10 @@ class Homographic_aug:
 
     def sample_homography(self, shape, **params):
         """-> (1,3,3) fp32 on ``self.device`` (homographic_augmentation.py:21-106)."""
+        return self.sample_homography_host(shape, **params).to(self.device)
+
+    def sample_homography_host(self, shape, **params):
+        """The same matrix, left on the host (the export loop batches the upload of all homographies of a group)."""
         src, dst = sample_corners(**params)
         wh = np.array(tuple(shape)[::-1], dtype=np.float64)[np.newaxis]
         try:
@@ -92,8 +96,7 @@ class Homographic_aug:
             M = cv2.getPerspectiveTransform(np.float32(src * wh), np.float32(dst * wh))
         except ImportError:  # same linear system, numpy solver
             M = perspective_from_corners(src * wh, dst * wh)
-        H = torch.inverse(torch.as_tensor(M, dtype=torch.float32).unsqueeze(0))  # 3x3 on the host: plumbing
-        return H.to(self.device)
+        return torch.inverse(torch.as_tensor(M, dtype=torch.float32).unsqueeze(0))  # 3x3 on the host: plumbing
 
     def sample_homographies_device(self, shape, count, seed=0, first_index=0, **params):
         """Batched device sampler: -> (H (count,3,3), H_inv (count,3,3)) fp32 CUDA tensors."""

@@ -12,6 +12,13 @@ whose result export.py:69 discards is not computed.
 Extension keys under ``homography_adaptation`` (optional): ``sampler`` 'device' (default, spn_sample_homographies)
 or 'numpy' (the reference's host sampler and RNG order), ``seed``, ``images_per_launch`` (default 1),
 ``max_forwards`` (forwards per encoder launch, default 128), ``streams`` (concurrent CUDA streams, default 1).
+
+Geometry: homographies that come from the host (the numpy sampler, or matrices passed in) go through
+``utils.kornia_geometry.sampling_matrices`` - the reference's own torch calls - and the kernels then follow kornia's
+fp32 coordinate chain operation for operation, so validity masks, counts and warped samples are bit-identical to the
+reference's CPU run.  Device-sampled homographies use ``spn_kornia_matrices`` (same algebra, device arithmetic).
+The device sampler is keyed by (seed, global image index * (num-1) + j): the homographies of an image depend only on
+its index in the dataset order (``first_index``), not on batching, resume state or rank.
 """
 import os
 from pathlib import Path
@@ -21,6 +28,7 @@ import torch
 
 from .. import settings
 from ..data.data_utils.homographic_augmentation import Homographic_aug
+from ..utils.kornia_geometry import sampling_matrices
 from ..utils.train_utils import move_to_device
 
 try:
@@ -49,11 +57,23 @@ class HomographyAdaptation:
             raise ValueError("homography_adaptation.valid_border_margin must be >= 1")
 
     def _homographies(self, NI, n_h, H, W, first_index):
+        """-> (NI,n_h,3,3) homographies: HOST tensors from the numpy sampler (the reference's RNG order, export.py:47),
+        DEVICE tensors from the device sampler."""
         if self.ha.get("sampler", "device") == "numpy":
-            hs = [self.sampler.sample_homography((H, W), **self.ha["params"]) for _ in range(NI * n_h)]
+            hs = [self.sampler.sample_homography_host((H, W), **self.ha["params"]) for _ in range(NI * n_h)]
             return torch.cat(hs).view(NI, n_h, 3, 3).contiguous()
         h, _ = self.sampler.sample_homographies_device((H, W), NI * n_h, seed=self.seed, first_index=first_index * n_h)
         return h.view(NI, n_h, 3, 3)
+
+    def _sampling_matrices(self, ctx, homographies, NI, n_h, H, W, dev):
+        """-> (h on the device, fwd, bwd): kornia's normalised sampling matrices for H and H^-1 (export.py:49-55,72)."""
+        if homographies.is_cuda and self.ha.get("geometry", "auto") != "host":
+            h = homographies.to(dev, torch.float32).contiguous().view(NI, n_h, 3, 3)
+            fwd, bwd = ctx.kornia_matrices(h, H, W)
+            return h, fwd, bwd
+        fwd, bwd = sampling_matrices(homographies, (H, W))           # the reference's torch calls on the host
+        pack = torch.stack([homographies.detach().to("cpu", torch.float32).reshape(-1, 3, 3), fwd, bwd]).to(dev)
+        return tuple(t.view(NI, n_h, 3, 3) for t in pack)
 
     @torch.no_grad()
     def heatmaps(self, images, homographies=None, enable_HA=True, first_index=0):
@@ -95,8 +115,7 @@ class HomographyAdaptation:
             return self.model.prob_heatmap(imgs, slot=slot), None
         if homographies is None:
             homographies = self._homographies(NI, n_h, H, W, first_index)
-        h = homographies.to(self.device, torch.float32).contiguous().view(NI, n_h, 3, 3)
-        hinv = ctx.invert3x3(h)                                                  # export.py:49
+        h, hinv, hback = self._sampling_matrices(ctx, homographies, NI, n_h, H, W, imgs.device)   # export.py:49 + kornia
         fused = self.model.mode != 0 and self.ha.get("fused_warp", True)         # tensor-core modes: warp inside conv kernel
         warped, mask = ctx.warp_batch(imgs, hinv, self.ha["valid_border_margin"], want_warped=not fused)  # export.py:51-66
         B = NI * (n_h + 1)
@@ -107,7 +126,7 @@ class HomographyAdaptation:
                 self.model.prob_heatmap_ha(imgs, hinv, s, e - s, mask=mask[s:e], out=probs[s:e], slot=slot)
             else:
                 self.model.prob_heatmap(warped[s:e], mask=mask[s:e], out=probs[s:e], slot=slot)
-        agg = ctx.ha_aggregate(probs.view(NI, n_h + 1, H, W), h, self.ha["valid_border_margin"],
+        agg = ctx.ha_aggregate(probs.view(NI, n_h + 1, H, W), hback, self.ha["valid_border_margin"],
                                self.ha["aggregation"])                           # export.py:72-77,106-114
         return agg, h
 
@@ -118,14 +137,15 @@ class HomographyAdaptation:
         ctx = self.model.native()
         NI, H, W = heat.shape
         max_kp = min(H * W, 16384)
-        r = ctx.box_nms(heat, float(self.dh["nms"]), 0.1, float(self.dh["det_thresh"]), int(self.dh["top_k"]),
-                        det_thresh=float(self.dh["det_thresh"]), want_map=False, max_kp=max_kp)
-        kp_h = torch.empty(r["kp"].shape, dtype=torch.int32, pin_memory=True)
-        cnt_h = torch.empty(r["kp_count"].shape, dtype=torch.int32, pin_memory=True)
-        kp_h.copy_(r["kp"], non_blocking=True)
-        cnt_h.copy_(r["kp_count"], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        with torch.cuda.device(heat.device):      # copies and the completion event go on the heatmap's device
+            r = ctx.box_nms(heat, float(self.dh["nms"]), 0.1, float(self.dh["det_thresh"]), int(self.dh["top_k"]),
+                            det_thresh=float(self.dh["det_thresh"]), want_map=False, max_kp=max_kp)
+            kp_h = torch.empty(r["kp"].shape, dtype=torch.int32, pin_memory=True)
+            cnt_h = torch.empty(r["kp_count"].shape, dtype=torch.int32, pin_memory=True)
+            kp_h.copy_(r["kp"], non_blocking=True)
+            cnt_h.copy_(r["kp_count"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(heat.device))
         return {"heat": heat, "kp": kp_h, "count": cnt_h, "event": ev, "max_kp": max_kp, "dev": r}
 
     def keypoints_wait(self, handle):

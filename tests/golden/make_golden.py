@@ -170,7 +170,40 @@ def main():
             refexport.K.warp_perspective(torch.ones_like(img), Hs[i:i + 1], dsize=(120, 160), mode="nearest", align_corners=True),
             O.erosion_kernel(3))
         steps[f"mask{i}"] = m[0, 0].numpy().astype(np.int32)
+    # the normalised sampling matrices kornia derives inside warp_perspective for H and H^-1 (what the device kernels
+    # take as input: LAPACK's inverse is not reproducible on the device, the coordinate chain after it is)
+    steps["ainv"] = torch.cat([kornia_shim._inverse_cast(kornia_shim.normalize_homography(Hs[i:i + 1], (120, 160), (120, 160)))
+                               for i in range(3)]).numpy()
+    steps["ainv_back"] = torch.cat([kornia_shim._inverse_cast(kornia_shim.normalize_homography(torch.inverse(Hs[i:i + 1]), (120, 160), (120, 160)))
+                                    for i in range(3)]).numpy()
     np.savez_compressed(OUT / "ha_step.npz", **steps)
+
+    # ---- 4b. many validity masks / counts (bit-exact gate for the geometry kernels), several sizes and margins ----
+    mm = {}
+    cases = [(240, 320, 3, 12, 31), (120, 160, 3, 12, 32), (64, 96, 2, 8, 33), (40, 72, 1, 8, 34), (96, 128, 4, 6, 35)]
+    for ci, (h, w, margin, n, seed) in enumerate(cases):
+        np.random.seed(seed)
+        Hc = torch.cat([aug.sample_homography((h, w), **HA_CFG["params"]) for _ in range(n)])
+        ones = torch.ones((1, 1, h, w))
+        ker = O.erosion_kernel(margin)
+        masks, counts, fw, bw = [], [], [], []
+        for i in range(n):
+            Hi = Hc[i:i + 1]
+            Hinv = torch.inverse(Hi)
+            mk = refexport.kornia.morphology.erosion(refexport.K.warp_perspective(ones, Hi, dsize=(h, w), mode="nearest", align_corners=True), ker)
+            ct = refexport.kornia.morphology.erosion(refexport.K.warp_perspective(ones, Hinv, dsize=(h, w), mode="nearest", align_corners=True), ker)
+            masks.append(mk[0, 0].numpy().astype(np.uint8))
+            counts.append(ct[0, 0].numpy().astype(np.uint8))
+            fw.append(kornia_shim._inverse_cast(kornia_shim.normalize_homography(Hi, (h, w), (h, w))))
+            bw.append(kornia_shim._inverse_cast(kornia_shim.normalize_homography(Hinv, (h, w), (h, w))))
+        mm[f"c{ci}_par"] = np.array([h, w, margin, n])
+        mm[f"c{ci}_H"] = Hc.numpy()
+        mm[f"c{ci}_ainv"] = torch.cat(fw).numpy()
+        mm[f"c{ci}_ainv_back"] = torch.cat(bw).numpy()
+        mm[f"c{ci}_mask"] = np.packbits(np.stack(masks), axis=-1)
+        mm[f"c{ci}_count"] = np.packbits(np.stack(counts), axis=-1)
+    mm["n"] = np.array(len(cases))
+    np.savez_compressed(OUT / "ha_masks.npz", **mm)
 
     # ---- 5. end-to-end ExportDetections (HA, 8 homographies, 120x160) ---------------------------
     sd = O.make_state_dict("magicpoint", seed=11, logit_gain=12.0)
@@ -202,8 +235,13 @@ def main():
     refexport.box_nms = orig_nms
     Homographic_aug.sample_homography = orig_sample
     kp = np.load(Path(exper, "outputs", "golden", "training", "img0.npy"))
-    np.savez_compressed(OUT / "ha_export.npz", image=img.numpy(), H=torch.cat(used_h).numpy(), agg=captured["agg"].numpy(),
-                        nms=captured["nms"].numpy(), keypoints=kp, seed=np.array(11), gain=np.array(12.0), np_seed=np.array(123))
+    Hu = torch.cat(used_h)
+    np.savez_compressed(OUT / "ha_export.npz", image=img.numpy(), H=Hu.numpy(), agg=captured["agg"].numpy(),
+                        nms=captured["nms"].numpy(), keypoints=kp, seed=np.array(11), gain=np.array(12.0), np_seed=np.array(123),
+                        ainv=torch.cat([kornia_shim._inverse_cast(kornia_shim.normalize_homography(Hu[i:i + 1], (120, 160), (120, 160)))
+                                        for i in range(len(Hu))]).numpy(),
+                        ainv_back=torch.cat([kornia_shim._inverse_cast(kornia_shim.normalize_homography(torch.inverse(Hu[i:i + 1]), (120, 160), (120, 160)))
+                                             for i in range(len(Hu))]).numpy())
     print("ha_export keypoints", kp.shape, kp.dtype)
 
     # ---- 6. HPatches-style exports: file layout --------------------------------------------------

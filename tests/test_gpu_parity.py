@@ -164,38 +164,70 @@ def test_forward_random_init_config1(P):
 
 
 # ------------------------------------------------------------------------------------------------ warp / masks
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
 def test_warp_batch_vs_golden_step(ctx, golden):
+    """ExportDetections.step warp part on the reference's own sampling matrices: masks BIT-EXACT, warped pixels
+    bit-exact as well (the kernel follows kornia's fp32 coordinate chain and ATen's bilinear arithmetic)."""
     g = golden("ha_step.npz")
-    img = torch.from_numpy(g["image"][0]).cuda()            # (1,H,W)
-    h = torch.from_numpy(g["H"]).cuda().view(1, 3, 3, 3).contiguous()
+    img = _dev(g["image"][0])                              # (1,H,W)
+    h = _dev(g["H"]).view(1, 3, 3, 3)
     hinv = ctx.invert3x3(h)
     assert rel_err(hinv.cpu().numpy()[0], torch.inverse(torch.from_numpy(g["H"])).numpy()) < 1e-5
-    warped, mask = ctx.warp_batch(img, hinv, 3)
+    warped, mask = ctx.warp_batch(img, _dev(g["ainv"]).view(1, 3, 3, 3), 3)
     assert np.array_equal(warped[0].cpu().numpy(), g["image"][0, 0]) and bool((mask[0] == 1).all())
     for i in range(3):
-        w = warped[1 + i].cpu().numpy()
-        assert np.abs(w - g[f"warped{i}"]).max() < 2e-4          # bilinear values (image in [0,1])
-        mm = mask[1 + i].cpu().numpy().astype(np.int32)
-        assert (mm != g[f"mask{i}"]).sum() <= 2, "eroded validity mask differs beyond boundary rounding"
+        assert np.array_equal(mask[1 + i].cpu().numpy().astype(np.int32), g[f"mask{i}"]), f"mask {i} not bit-exact"
+        assert np.array_equal(warped[1 + i].cpu().numpy(), g[f"warped{i}"]), f"warped image {i} not bit-exact"
+    # count = the mask of the warp by H^-1 (export.py:55,65)
+    _, cnt = ctx.warp_batch(img, _dev(g["ainv_back"]).view(1, 3, 3, 3), 3, want_warped=False)
+    for i in range(3):
+        assert np.array_equal(cnt[1 + i].cpu().numpy().astype(np.int32), g[f"count{i}"]), f"count {i} not bit-exact"
+
+
+def test_masks_and_counts_bit_exact_vs_golden(ctx, golden):
+    """46 reference masks + 46 counts at five image sizes and four erosion margins: array_equal."""
+    g = golden("ha_masks.npz")
+    for ci in range(int(g["n"])):
+        h, w, margin, n = (int(v) for v in g[f"c{ci}_par"])
+        img = torch.zeros((1, h, w), device="cuda")
+        want_m = np.unpackbits(g[f"c{ci}_mask"], axis=-1)[..., :w]
+        want_c = np.unpackbits(g[f"c{ci}_count"], axis=-1)[..., :w]
+        _, m = ctx.warp_batch(img, _dev(g[f"c{ci}_ainv"]).view(1, n, 3, 3), margin, want_warped=False)
+        _, c = ctx.warp_batch(img, _dev(g[f"c{ci}_ainv_back"]).view(1, n, 3, 3), margin, want_warped=False)
+        assert np.array_equal(m[1:].cpu().numpy(), want_m), f"case {ci} ({h}x{w}, margin {margin}): masks differ"
+        assert np.array_equal(c[1:].cpu().numpy(), want_c), f"case {ci} ({h}x{w}, margin {margin}): counts differ"
+        assert 0.05 < want_m.mean() < 0.99                       # the cases do cut the image
+        # the device-arithmetic matrices (spn_kornia_matrices) agree with the reference's to a few ulp
+        fwd, bwd = ctx.kornia_matrices(_dev(g[f"c{ci}_H"]), h, w)
+        assert rel_err(fwd.cpu().numpy(), g[f"c{ci}_ainv"]) < 2e-5 and rel_err(bwd.cpu().numpy(), g[f"c{ci}_ainv_back"]) < 2e-5
+        _, m2 = ctx.warp_batch(img, fwd.view(1, n, 3, 3), margin, want_warped=False)
+        assert (m2[1:].cpu().numpy() != want_m).mean() < 2e-4    # ... so their masks differ on boundary pixels at most
 
 
 def test_ha_aggregate_vs_golden_step(ctx, golden):
     g = golden("ha_step.npz")
     H, W = 120, 160
-    h = torch.from_numpy(g["H"]).cuda().view(1, 3, 3, 3).contiguous()
-    img = torch.from_numpy(g["image"][0]).cuda()
-    warped, mask = ctx.warp_batch(img, ctx.invert3x3(h), 3)
+    img = _dev(g["image"][0])
+    warped, mask = ctx.warp_batch(img, _dev(g["ainv"]).view(1, 3, 3, 3), 3)
     probs = (0.25 + 0.5 * warped) * mask                        # the golden step's fake model, times the mask
     probs[0] = 0.0                                              # golden step started from zeros (export.py:76)
-    agg = ctx.ha_aggregate(probs.view(1, 4, H, W).contiguous(), h, 3, "sum")[0].cpu().numpy()
+    back = _dev(g["ainv_back"]).view(1, 3, 3, 3)
+    agg = ctx.ha_aggregate(probs.view(1, 4, H, W).contiguous(), back, 3, "sum")[0].cpu().numpy()
     want_sum = sum(g[f"proj{i}"] for i in range(3))
     want_cnt = 1 + sum(g[f"count{i}"] for i in range(3))
     want = want_sum / want_cnt
-    bad = np.abs(agg - want) > 1e-4 * np.abs(want).max()
-    assert bad.mean() < 2e-4, f"{bad.sum()} pixels off"         # only mask-boundary pixels may differ
-    mx = ctx.ha_aggregate(probs.view(1, 4, H, W).contiguous(), h, 3, "max")[0].cpu().numpy()
+    assert rel_err(agg, want) < STRICT                           # every pixel, mask borders included
+    mx = ctx.ha_aggregate(probs.view(1, 4, H, W).contiguous(), back, 3, "max")[0].cpu().numpy()
     want_mx = np.max(np.stack([g[f"proj{i}"] for i in range(3)]), 0)
-    assert (np.abs(mx - want_mx) > 1e-4).mean() < 2e-4
+    assert rel_err(mx, want_mx) < STRICT
+    # single projections are bit-exact: with one homography and a zero identity slot, 2 * mean = proj * count
+    for i in range(3):
+        p1 = torch.stack([torch.zeros_like(probs[0]), probs[1 + i]]).view(1, 2, H, W).contiguous()
+        one = ctx.ha_aggregate(p1, back[:, i:i + 1].contiguous(), 3, "max")[0].cpu().numpy()
+        assert np.array_equal(one, g[f"proj{i}"]), f"projection {i} not bit-exact"
 
 
 def test_warp_identity_and_shift_properties(ctx):
@@ -205,15 +237,17 @@ def test_warp_identity_and_shift_properties(ctx):
     eye = torch.eye(3, device="cuda")
     shift = torch.tensor([[1.0, 0, 5], [0, 1, -3], [0, 0, 1]], device="cuda")   # H: p -> p + (5,-3)
     h = torch.stack([eye, shift]).view(1, 2, 3, 3).contiguous()
-    warped, mask = ctx.warp_batch(img, ctx.invert3x3(h), 3)
-    assert torch.equal(warped[1], img[0]) and bool((mask[1] == 1).all())
+    fwd, bwd = ctx.kornia_matrices(h, H, W)
+    warped, mask = ctx.warp_batch(img, fwd, 3)
+    # normalised-space fp32 coordinates land within ~1e-4 px of the integer grid (as in the reference): near-exact
+    assert float((warped[1] - img[0]).abs().max()) < 2e-4 and bool((mask[1] == 1).all())
     w2 = warped[2].cpu().numpy()
     src = img[0].cpu().numpy()
-    assert np.array_equal(w2[:-3, 5:], src[3:, :-5])           # out(p) = src(p - (5,-3))
-    assert np.all(w2[:, :5] == 0) and np.all(w2[-3:, :] == 0)
+    assert np.abs(w2[:-3, 5:] - src[3:, :-5]).max() < 2e-4      # out(p) = src(p - (5,-3))
+    assert np.all(np.abs(w2[:, :4]) < 2e-4) and np.all(np.abs(w2[-2:, :]) < 2e-4)
     probs = torch.stack([img[0], warped[1] * mask[1]]).view(1, 2, H, W).contiguous()
-    agg = ctx.ha_aggregate(probs, eye.view(1, 1, 3, 3).contiguous(), 3, "sum")
-    assert float((agg[0] - img[0]).abs().max()) < 1e-7           # mean of two identical maps
+    agg = ctx.ha_aggregate(probs, bwd[:, :1].contiguous(), 3, "sum")
+    assert float((agg[0] - img[0]).abs().max()) < 3e-4           # mean of two (near-)identical maps
 
 
 # ------------------------------------------------------------------------------------------------ sampler
@@ -255,8 +289,7 @@ def test_ha_export_end_to_end_vs_golden(P, golden, tmp_path, monkeypatch):
     img = torch.from_numpy(g["image"]).cuda()
     heat, _ = eng.heatmaps(img, homographies=torch.from_numpy(g["H"]).view(1, 7, 3, 3))
     agg = heat[0].cpu().numpy()
-    bad = np.abs(agg - g["agg"]) > STRICT * np.abs(g["agg"]).max()
-    assert bad.mean() < 5e-4, f"{bad.sum()} pixels of the aggregated heatmap off by more than 1e-4 relative"
+    assert rel_err(agg, g["agg"]) < STRICT, "aggregated heatmap (all pixels, mask borders included)"
     kp = eng.keypoints(heat)[0]
     assert kp.dtype == np.int64 and kp.shape[1] == 2
     a, b = keypoint_agreement(kp, g["keypoints"])
@@ -296,8 +329,7 @@ def test_ha_full_size_vs_oracle(P):
     eng = HomographyAdaptation(cfg, m, "cuda")
     heat, _ = eng.heatmaps(img.cuda(), homographies=want["homographies"].view(1, 5, 3, 3))
     agg = heat[0].cpu().numpy()
-    bad = np.abs(agg - want["mean_prob"].numpy()) > STRICT * float(want["mean_prob"].abs().max())
-    assert bad.mean() < 5e-4
+    assert rel_err(agg, want["mean_prob"].numpy()) < STRICT
     a, b = keypoint_agreement(eng.keypoints(heat)[0], want["keypoints"])
     assert a >= 0.99 and b >= 0.99
     # two images per launch give the same result as one at a time (batching is transparent)
@@ -351,8 +383,7 @@ def test_ha_max_aggregation_and_no_ha_vs_oracle(P, tmp_path, monkeypatch):
     eng = HomographyAdaptation(cfg, m, "cuda")
     heat, _ = eng.heatmaps(img.cuda(), homographies=want["homographies"].view(1, 4, 3, 3))
     ref = want["mean_prob"].numpy()
-    bad = np.abs(heat[0].cpu().numpy() - ref) > STRICT * np.abs(ref).max()
-    assert bad.mean() < 1e-3
+    assert rel_err(heat[0].cpu().numpy(), ref) < STRICT
     kp = eng.keypoints(heat)[0]
     assert len(kp) == 40 == len(want["keypoints"])                 # top_k honoured
     a, b = keypoint_agreement(kp, want["keypoints"])

@@ -88,8 +88,47 @@ def test_ha_fast_mode_keypoints_vs_golden(golden):
     err = rel_err(heat[0].cpu().numpy(), g["agg"])
     a, b = keypoint_agreement(eng.keypoints(heat)[0], g["keypoints"])
     print(f"fast-mode HA: heatmap rel err {err:.2e}, keypoints within 1px {a:.4f}/{b:.4f}")
-    assert err < 2e-2
-    assert a >= 0.97 and b >= 0.97
+    assert err < FAST                      # north_star: 5e-3 where 16-bit convolutions are enabled and stated
+    assert a >= 0.99 and b >= 0.99         # north_star: >= 99 % within 1 px, both directions
+
+
+def _random_init_sd():
+    """The bench's exact model: torch default init under torch.manual_seed(0) (bench.py: random_init_state_dict)."""
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    torch.manual_seed(0)
+    return {k: v.detach().cpu() for k, v in get_model(copy.deepcopy(MP_MODEL), "cpu").state_dict().items()}
+
+
+@pytest.mark.parametrize("weights", ["peaky", "random_init"])
+def test_ha_fast_mode_headline_workload_vs_oracle(weights):
+    """The headline workload in the headline mode: 240x320, f16 convolutions, det_thresh 0.015, NMS 4, 25 homographies
+    from the reference's numpy sampler, against the fp32 CPU oracle of ExportDetections.homography_adaptation
+    (export.py:82-129).  'random_init' is the bench's own model (flat ~1/65 heatmap, the threshold straddles the mean).
+    Gates = north_star: aggregated heatmap 5e-3 relative over ALL pixels, keypoints >= 99 % within 1 px both ways."""
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import HomographyAdaptation
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    H, W, n_h = 240, 320, 25
+    if weights == "peaky":
+        sd = O.make_state_dict("magicpoint", seed=5, logit_gain=10.0)
+        img = torch.from_numpy(smooth_image(H, W, 8))[None, None]
+    else:
+        sd = _random_init_sd()
+        img = torch.rand((1, 1, H, W), generator=torch.Generator().manual_seed(0))
+    ha = dict(copy.deepcopy(HA_CFG), num=n_h + 1)
+    c = dict(copy.deepcopy(MP_MODEL), precision="f16")
+    np.random.seed(2)
+    want = O.homography_adaptation(sd, img, {"homography_adaptation": ha, "model": copy.deepcopy(MP_MODEL)}, nms_fn=O.box_nms_c)
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    eng = HomographyAdaptation({"homography_adaptation": ha, "model": c}, m, "cuda")
+    heat, _ = eng.heatmaps(img.cuda(), homographies=want["homographies"].view(1, n_h, 3, 3))
+    err = rel_err(heat[0].cpu().numpy(), want["mean_prob"].numpy())
+    kp = eng.keypoints(heat)[0]
+    a, b = keypoint_agreement(kp, want["keypoints"])
+    print(f"{weights}: f16 HA heatmap rel err {err:.2e}, {len(kp)} vs {len(want['keypoints'])} keypoints, within 1px {a:.4f}/{b:.4f}")
+    assert len(want["keypoints"]) > 1000
+    assert err < FAST
+    assert a >= 0.99 and b >= 0.99
 
 
 def test_fused_front_end_matches_unfused(monkeypatch):
@@ -105,8 +144,8 @@ def test_fused_front_end_matches_unfused(monkeypatch):
     ctx = m.native()
     for (NI, H, W, n_h) in [(2, 240, 320, 3), (1, 120, 160, 5), (3, 40, 72, 2)]:
         imgs = torch.from_numpy(np.stack([smooth_image(H, W, 60 + i) for i in range(NI)])).cuda()
-        h, hinv = ctx.sample_homographies(HA_CFG["params"], seed=3, first_index=0, count=NI * n_h, H=H, W=W)
-        hinv = hinv.view(NI, n_h, 3, 3)
+        h, _ = ctx.sample_homographies(HA_CFG["params"], seed=3, first_index=0, count=NI * n_h, H=H, W=W)
+        hinv = ctx.kornia_matrices(h, H, W)[0].view(NI, n_h, 3, 3)      # kornia sampling matrices of the warps
         warped, mask = ctx.warp_batch(imgs, hinv, 3)
         B = NI * (n_h + 1)
         monkeypatch.setenv("SPN_TC_NOFUSE", "1")

@@ -163,3 +163,20 @@ def test_weights_key_tracks_parameter_updates():
     with torch.no_grad():
         m.detector_head.convPb.conv2d.bias.add_(1.0)
     assert m._weights_key() != k1
+
+
+def test_kornia_geometry_mirror_matches_the_shim():
+    """utils/kornia_geometry.sampling_matrices (what the binding uploads for host homographies) == the matrices the
+    restated kornia.warp_perspective builds (oracle/kornia_shim.py), bit for bit, and == the committed reference bits."""
+    from oracle import kornia_shim as K
+    from superpoint_nerf_pytorch_b200.utils.kornia_geometry import sampling_matrices
+    g = np.load(ROOT / "tests" / "golden" / "ha_masks.npz")
+    for ci in range(int(g["n"])):
+        h, w, _margin, n = (int(v) for v in g[f"c{ci}_par"])
+        Hc = torch.from_numpy(g[f"c{ci}_H"])
+        fwd, bwd = sampling_matrices(Hc, (h, w))
+        for i in range(n):
+            a = K._inverse_cast(K.normalize_homography(Hc[i:i + 1], (h, w), (h, w)))[0]
+            b = K._inverse_cast(K.normalize_homography(torch.inverse(Hc[i:i + 1]), (h, w), (h, w)))[0]
+            assert torch.equal(fwd[i], a) and torch.equal(bwd[i], b)
+        assert np.array_equal(fwd.numpy(), g[f"c{ci}_ainv"]) and np.array_equal(bwd.numpy(), g[f"c{ci}_ainv_back"])

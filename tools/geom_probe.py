@@ -9,7 +9,7 @@ ctx = _native.Context(0)
 NI, NH, H, W = 16, 99, 240, 320
 hp = dict(bench.HA_CFG["params"])
 h, hinv = ctx.sample_homographies(hp, 1234, 0, NI * NH, H, W)
-h, hinv = h.view(NI, NH, 3, 3), hinv.view(NI, NH, 3, 3)
+hinv, h = (t.view(NI, NH, 3, 3) for t in ctx.kornia_matrices(h, H, W))   # fwd (masks), bwd (aggregate)
 imgs = torch.rand((NI, H, W), device=dev)
 probs = torch.rand((NI, NH + 1, H, W), device=dev)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
