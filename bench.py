@@ -14,7 +14,9 @@ Prints ONE JSON line (rank 0).  `value` = images/s with the images already resid
 the public API (HomographyAdaptation.__call__, i.e. what ExportDetections runs) from pinned HOST images to HOST
 keypoint arrays, copies inside the timed region.  `roofline` = the dominant kernel (block_2 convolution) timed with
 CUDA events inside the library during the timed region; `kernels` lists the same for the other kernels.
-`cpu_baseline` (N=1, rank 0) = the oracle port of the reference timed on the host cores on a bounded sample.
+`cpu_baseline` (N=1, rank 0) = the oracle port of the reference timed on the host cores on a bounded sample (1 image x
+25 of 100 homographies); `gpu_reference` = the same port with device="cuda" (stock cuDNN with torch's TF32 default,
+torchvision's CUDA nms, 100 sequential batch-1 steps) - the honest GPU bar next to the CPU figure.
 
 `--impl reference` times the reference's CPU path (oracle port, the reference is pure Python) on the host cores.
 """
@@ -54,14 +56,16 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustain
 
 def ncu_block2_traffic_per_forward(fused=True):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch in the committed `ncu --set full`
-    capture (profiles/r1_kernels_final.json, 100 forwards per launch) -> bytes per forward, or None."""
-    try:
-        ks = json.loads((ROOT / "profiles" / "r1_kernels_final.json").read_text())
-        pat = "front_tc_kernel" if fused else "conv_tc_kernel<9>"
-        k = max((k for k in ks if pat in k["kernel"]), key=lambda k: k["time_us"])
-        return (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6 / 100.0
-    except Exception:
-        return None
+    capture (latest profiles/r*_kernels_final.json, 100 forwards per launch) -> bytes per forward, or None."""
+    for name in ("r2_kernels_final.json", "r1_kernels_final.json"):
+        try:
+            ks = json.loads((ROOT / "profiles" / name).read_text())
+            pat = "front_tc_kernel" if fused else "conv_tc_kernel<9>"
+            k = max((k for k in ks if pat in k["kernel"]), key=lambda k: k["time_us"])
+            return (k["dram_read_MB"] + k["dram_write_MB"]) * 1e6 / float(k.get("forwards_per_launch", 100))
+        except Exception:
+            continue
+    return None
 
 
 def peaks():
@@ -122,9 +126,10 @@ def random_init_state_dict():
     return {k: v.detach().cpu() for k, v in get_model(copy.deepcopy(MODEL_CFG), "cpu").state_dict().items()}
 
 
-def cpu_reference_sample(n_hom: int, threads: int | None = None):
+def cpu_reference_sample(n_hom: int, threads: int | None = None, device: str | None = None):
     """Time the oracle port of ExportDetections (full forward incl. the in-model NMS the reference pays for and discards)
-    on the host cores: ONE 240x320 image with `n_hom` homographies; extrapolate linearly to 100."""
+    on the host cores - or, with ``device="cuda"``, the same code on the GPU the way the reference would run there
+    (cuDNN, TF32 default, torchvision CUDA nms): ONE 240x320 image with `n_hom` homographies; extrapolate linearly to 100."""
     import numpy as np
     import torch
 
@@ -142,13 +147,20 @@ def cpu_reference_sample(n_hom: int, threads: int | None = None):
     g = torch.Generator().manual_seed(0)
     img = torch.rand((1, 1, H, W), generator=g)
     np.random.seed(0)
+    if device is not None:   # warm-up: cuDNN autotuning, torchvision op loading, allocator
+        O.homography_adaptation(sd, img, {**cfg, "homography_adaptation": dict(cfg["homography_adaptation"], num=3)},
+                                full_forward=True, device=device)
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
-    O.homography_adaptation(sd, img, cfg, full_forward=True)
+    O.homography_adaptation(sd, img, cfg, full_forward=True, device=device)
+    if device is not None:
+        torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     per_forward = dt / n_hom
+    where = "host cores" if device is None else f"{device} (cuDNN, allow_tf32={torch.backends.cudnn.allow_tf32}, torchvision CUDA nms)"
     return {"seconds": dt, "img_per_s": 1.0 / (per_forward * NUM_H), "cores": torch.get_num_threads(),
             "sample": f"1 image x {n_hom} of {NUM_H} homographies (240x320, full model forward incl. in-model NMS, "
-                      f"kornia-shim warps), linearly extrapolated to {NUM_H}"}
+                      f"kornia-shim warps) on {where}, linearly extrapolated to {NUM_H}"}
 
 
 def run_reference(args):
@@ -370,6 +382,13 @@ def run_native(args):
     if world == 1 and not args.no_cpu_baseline:
         c = cpu_reference_sample(args.ref_homographies)
         line["cpu_baseline"] = {"value": c["img_per_s"], "unit": "img/s", "cores": c["cores"], "kind": "port", "sample": c["sample"]}
+        try:    # the reference's own code path with device="cuda": the honest GPU bar
+            gr = cpu_reference_sample(args.ref_homographies, device=str(dev))
+            line["gpu_reference"] = {"value": gr["img_per_s"], "unit": "img/s", "kind": "port", "device": "B200", "sample": gr["sample"],
+                                     "note": "not comparable bit for bit: TF32 cuDNN convolutions; 100 sequential batch-1 "
+                                             "steps, each with the in-model NMS that export.py:69 discards"}
+        except Exception as e:   # e.g. torchvision built without CUDA ops
+            line["gpu_reference"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -384,10 +403,12 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SPN_B200_PRECISION", "f16"), choices=["fp32", "f16", "bf16"],
                     help="f16 (default): tcgen05 convolutions, fp16 operands / fp32 accumulate, 5e-3 parity gate; "
                          "fp32: strict FFMA convolutions, 1e-4 parity gate")
-    ap.add_argument("--images-per-step", type=int, default=16)
+    ap.add_argument("--images-per-step", type=int, default=128,
+                    help="images per GPU per step; 128 makes a step ~170 ms so the timed region of the default run is > 3 s "
+                         "(the sustained, power-capped regime rather than a burst)")
     ap.add_argument("--max-forwards", type=int, default=100)
     ap.add_argument("--streams", type=int, default=1)
-    ap.add_argument("--ref-homographies", type=int, default=6, help="homographies in the bounded CPU sample")
+    ap.add_argument("--ref-homographies", type=int, default=25, help="homographies in the bounded CPU sample (of 100)")
     ap.add_argument("--steps-ref", type=int, default=1)
     ap.add_argument("--warmup-ref", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -60,6 +60,11 @@ SPN_API int spn_version(void);
 SPN_API int spn_create(spn_ctx** out, int device);
 SPN_API int spn_destroy(spn_ctx* ctx);
 
+/* A/B switches of the tensor-core path (read when a launch is planned, never from the environment): "fold" (3x3 layers
+ * with the horizontal taps folded into N = 192), "fuse_front" (warp + block_1 + block_2 in one kernel), "fuse_head"
+ * (convPb + softmax + depth-to-space in one kernel), "pdl" (programmatic dependent launch).  All default to 1. */
+SPN_API int spn_set_option(spn_ctx* ctx, const char* name, int value);
+
 /* BN fold + pack + upload of one VGG_Block (conv2d + BatchNorm2d eval, eps as given).
  * Replaces nn.Conv2d/nn.BatchNorm2d parameter storage (VGG_Backbone.py:11-14) as loaded by engine.py:108-117.
  * h_w [cout][cin][k][k], h_b/h_gamma/h_beta/h_mean/h_var [cout] are HOST fp32 arrays. */

@@ -293,10 +293,10 @@ def erosion_kernel(margin):
 def ha_masks(H, shape, margin):
     """mask / count of one step (export.py:49-66): nearest warps of ones by H and H^-1, eroded, int32 (1,H,W)."""
     H_inv = torch.inverse(H)
-    ones = torch.ones((1, 1, *shape), dtype=torch.float32)
+    ones = torch.ones((1, 1, *shape), dtype=torch.float32, device=H.device)
     mask = K.warp_perspective(ones, H, dsize=shape, mode="nearest", align_corners=True)
     count = K.warp_perspective(ones, H_inv, dsize=shape, mode="nearest", align_corners=True)
-    ker = erosion_kernel(margin)
+    ker = erosion_kernel(margin).to(H.device)
     mask = K.erosion(mask, ker).to(torch.int32).squeeze(1)
     count = K.erosion(count, ker).to(torch.int32).squeeze(1)
     return mask, count, H_inv
@@ -317,14 +317,19 @@ def ha_step(prob_fn, image, H, margin):
 
 
 @torch.no_grad()
-def homography_adaptation(sd, image, config, homographies=None, full_forward=False, nms_fn=None):
+def homography_adaptation(sd, image, config, homographies=None, full_forward=False, nms_fn=None, device=None):
     """ExportDetections.homography_adaptation body for one image (export.py:93-125).
 
     image (1,1,H,W) fp32.  ``homographies``: optional (num-1,3,3) fp32; when None they are drawn with
     ``sample_homography`` from numpy's global RNG, one per step, as the reference does (export.py:47).
     ``full_forward=True`` also runs the in-model box_nms whose output export.py:69 discards (used for the
     CPU baseline so that it pays what the reference pays).
+    ``device``: run the same code on that torch device (the reference with ``device="cuda"``: cuDNN convolutions with
+    torch's TF32 default, torchvision's CUDA nms) - used for bench.py's reference-on-GPU figure only.
     Returns dict(mean_prob (H,W), nms_prob (H,W), keypoints (N,2) int64, homographies (num-1,3,3))."""
+    if device is not None:
+        sd = {k: v.to(device) for k, v in sd.items()}
+        image = image.to(device)
     ha = config["homography_adaptation"]
     mcfg = config["model"]
     dh = mcfg["detector_head"]
@@ -340,7 +345,7 @@ def homography_adaptation(sd, image, config, homographies=None, full_forward=Fal
     counts = [torch.ones_like(probs[0])]
     used = []
     for i in range(ha["num"] - 1):
-        H = homographies[i:i + 1] if homographies is not None else sample_homography(shape, **ha["params"])
+        H = (homographies[i:i + 1] if homographies is not None else sample_homography(shape, **ha["params"])).to(image.device)
         used.append(H)
         proj, count, _, _ = ha_step(prob_fn, image, H, ha["valid_border_margin"])
         probs.append(proj)
@@ -355,8 +360,8 @@ def homography_adaptation(sd, image, config, homographies=None, full_forward=Fal
     nms_fn = nms_fn or box_nms
     nmsp = nms_fn(agg[0], dh["nms"], min_prob=dh["det_thresh"], keep_top_k=dh["top_k"])
     kp = torch.nonzero((nmsp >= dh["det_thresh"]).to(torch.int32), as_tuple=False)
-    return {"mean_prob": agg[0], "nms_prob": nmsp, "keypoints": kp.numpy(),
-            "homographies": torch.cat(used, 0) if used else torch.zeros((0, 3, 3))}
+    return {"mean_prob": agg[0], "nms_prob": nmsp, "keypoints": kp.cpu().numpy(),
+            "homographies": torch.cat(used, 0).cpu() if used else torch.zeros((0, 3, 3))}
 
 
 # --------------------------------------------------------------------------------------------

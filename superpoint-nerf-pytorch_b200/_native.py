@@ -40,6 +40,7 @@ PROTOTYPES = {
     "spn_version": (_i, []),
     "spn_create": (_i, [C.POINTER(_vp), _i]),
     "spn_destroy": (_i, [_vp]),
+    "spn_set_option": (_i, [_vp, C.c_char_p, _i]),
     "spn_pack_weights": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
     "spn_conv_layer": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "spn_encoder_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -149,6 +150,10 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, name: str, value: int):
+        """A/B switches of the tensor-core path: 'fold', 'fuse_front', 'fuse_head', 'pdl' (all default 1)."""
+        self._call("spn_set_option", self.handle, name.encode(), int(value))
 
     @property
     def launches(self) -> int:

@@ -357,7 +357,7 @@ int spn_launch_conv_fold(spn_ctx* ctx, int layer, int mode, const void* in, void
   grid = grid / p.cout_slices * p.cout_slices;
   if (grid < p.cout_slices) grid = p.cout_slices;
   SpnProfScope prof(ctx, layer, s);
-  SPN_CUDA(spn_launch_pdl(conv_fold_kernel, dim3(grid), dim3(kThreads), dyn, s, tmap, p));
+  SPN_CUDA(spn_launch_pdl(ctx->opt_pdl != 0, conv_fold_kernel, dim3(grid), dim3(kThreads), dyn, s, tmap, p));
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }

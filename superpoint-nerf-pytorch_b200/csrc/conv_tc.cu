@@ -399,10 +399,8 @@ int launch_conv_tc(spn_ctx* ctx, int layer, int mode, const void* in, void* out,
   TcState* st = tc_state(ctx);
   const SpnLayer& L = ctx->layers[layer];
   const int bf = mode == SPN_MODE_BF16 ? 1 : 0;
-  if (L.ks == 3 && out_mode == 0) {  // 3x3 layers: horizontal taps folded into N (conv_fold.cu) unless SPN_TC_FOLD=0
-    const char* fold = getenv("SPN_TC_FOLD");
-    if (!fold || atoi(fold)) return spn_launch_conv_fold(ctx, layer, mode, in, out, n_img, H, W, relu, pool, s);
-  }
+  if (L.ks == 3 && out_mode == 0 && ctx->opt_fold)  // 3x3 layers: horizontal taps folded into N (conv_fold.cu)
+    return spn_launch_conv_fold(ctx, layer, mode, in, out, n_img, H, W, relu, pool, s);
   if (!L.w16[bf] || !st->bias_pad[layer]) { spn_set_error("layer %d has no tensor-core weights", layer); return SPN_E_STATE; }
   SPN_REQUIRE(L.cin % 64 == 0, "tensor-core conv needs Cin %% 64 == 0 (layer %d has %d)", layer, L.cin);
   int rc = get_encode(st);
@@ -573,9 +571,8 @@ int spn_tc_encoder_slots(spn_ctx* ctx, const float* d_images, const float* d_hin
   char* Bq = A + pl.a;
   char* F = Bq + pl.b;
   const int bf = mode == SPN_MODE_BF16 ? 1 : 0;
-  const char* nofuse = getenv("SPN_TC_NOFUSE");
-  if (nofuse && atoi(nofuse)) {
-    SPN_REQUIRE(!d_hinv, "SPN_TC_NOFUSE: the unfused path takes already-warped images");
+  if (!ctx->opt_fuse_front) {
+    SPN_REQUIRE(!d_hinv, "option fuse_front = 0: the unfused path takes already-warped images");
     {
       SpnProfScope prof(ctx, SPN_L_BLOCK1, s);
       dim3 g(spn_cdiv(W, 32 * kC1Px), spn_cdiv(H, kC1Rows), B);

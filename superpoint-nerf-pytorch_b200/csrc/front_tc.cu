@@ -365,11 +365,10 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
   const size_t dyn = (size_t)kW2Bytes + kW1Bytes + kNA1 * kA1Bytes + kOnesBytes + (size_t)kStages * kStageBytes + 1024;
   const long long tiles = (long long)n_slots * p.tiles_x * p.tiles_y;
   const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-  const int dbg = getenv("SPN_FRONT_DBG") ? atoi(getenv("SPN_FRONT_DBG")) : 0;
   void (*kern)(const FrontParams) = front_tc_kernel<0>;
-  switch (dbg) {
+#ifdef SPN_FRONT_DBG_BUILD  // diagnostic build only (tools/front_probe.py): role knock-out instantiations, wrong results
+  switch (ctx->opt_front_variant) {
     case 0: break;
-#ifdef SPN_FRONT_DBG_BUILD
     case 3: kern = front_tc_kernel<3>; break;
     case 12: kern = front_tc_kernel<12>; break;
     case 16: kern = front_tc_kernel<16>; break;
@@ -380,12 +379,12 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
     case 108: kern = front_tc_kernel<108>; break;
     case 99: kern = front_tc_kernel<99>; break;
     case 111: kern = front_tc_kernel<111>; break;
-#endif
-    default: spn_set_error("SPN_FRONT_DBG=%d is not compiled in", dbg); return SPN_E_INVALID;
+    default: spn_set_error("front_variant %d is not compiled in", ctx->opt_front_variant); return SPN_E_INVALID;
   }
+#endif
   SPN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   SpnProfScope prof(ctx, SPN_L_BLOCK2, s);
-  SPN_CUDA(spn_launch_pdl(kern, dim3(grid), dim3(kThreads), dyn, s, p));
+  SPN_CUDA(spn_launch_pdl(ctx->opt_pdl != 0, kern, dim3(grid), dim3(kThreads), dyn, s, p));
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }

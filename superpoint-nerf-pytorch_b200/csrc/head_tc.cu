@@ -274,7 +274,7 @@ int spn_launch_head_tc(spn_ctx* ctx, int mode, const void* in, int n_img, int Hc
   const long long tiles = (long long)n_img * p.tiles_x * p.tiles_y;
   const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
   SpnProfScope prof(ctx, SPN_L_CONVPB, s);
-  SPN_CUDA(spn_launch_pdl(head_tc_kernel, dim3(grid), dim3(kThreads), dyn, s, tmap, p));
+  SPN_CUDA(spn_launch_pdl(ctx->opt_pdl != 0, head_tc_kernel, dim3(grid), dim3(kThreads), dyn, s, tmap, p));
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }

@@ -83,6 +83,17 @@ extern "C" int spn_destroy(spn_ctx* ctx) {
   return SPN_OK;
 }
 
+extern "C" int spn_set_option(spn_ctx* ctx, const char* name, int value) {
+  SPN_REQUIRE(ctx && name, "spn_set_option: null pointer");
+  struct { const char* n; int* v; } opts[] = {{"fold", &ctx->opt_fold}, {"fuse_front", &ctx->opt_fuse_front},
+                                               {"fuse_head", &ctx->opt_fuse_head}, {"pdl", &ctx->opt_pdl},
+                                               {"front_variant", &ctx->opt_front_variant}};
+  for (auto& o : opts)
+    if (!strcmp(o.n, name)) { *o.v = value; return SPN_OK; }
+  spn_set_error("spn_set_option: unknown option '%s' (fold, fuse_front, fuse_head, pdl)", name);
+  return SPN_E_INVALID;
+}
+
 extern "C" int64_t spn_launch_count(spn_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 extern "C" int spn_profile_enable(spn_ctx* ctx, int enable) {
@@ -251,8 +262,7 @@ extern "C" int spn_detector_head_forward(spn_ctx* ctx, int B, int H, int W, int 
     if ((rc = spn_conv_fp32(ctx, SPN_L_CONVPA, (const float*)ctx->feat, A, B, Hc, Wc, true, false, s))) return rc;
     if ((rc = spn_conv_fp32(ctx, SPN_L_CONVPB, A, logits, B, Hc, Wc, false, false, s))) return rc;
   } else {
-    const char* nofuse = getenv("SPN_TC_NOHEADFUSE");
-    if (!(nofuse && atoi(nofuse)) && ctx->layers[SPN_L_CONVPB].w16f[mode == SPN_MODE_BF16 ? 1 : 0])
+    if (ctx->opt_fuse_head && ctx->layers[SPN_L_CONVPB].w16f[mode == SPN_MODE_BF16 ? 1 : 0])
       return spn_tc_detector_head_fused(ctx, B, H, W, mode, d_mask, d_logits, d_prob, s);  // convPb + softmax fused
     if (!logits) logits = spn_tc_logits_scratch(ctx, B, H, W);
     if ((rc = spn_tc_detector_head(ctx, B, H, W, mode, logits, s))) return rc;

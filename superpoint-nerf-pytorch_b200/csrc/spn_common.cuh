@@ -58,6 +58,12 @@ struct spn_ctx {
   void* feat = nullptr;     // points into ws
   int64_t launches = 0;
   void* tc = nullptr;       // tcgen05 path state (conv_tc.cu)
+  // options (spn_set_option): A/B switches of the tensor-core path, all on by default
+  int opt_fold = 1;         // 3x3 layers: horizontal taps folded into N (conv_fold.cu) instead of nine descriptors
+  int opt_fuse_front = 1;   // warp + block_1 + block_2 in one kernel (front_tc.cu)
+  int opt_fuse_head = 1;    // convPb + softmax + depth-to-space in one kernel (head_tc.cu)
+  int opt_pdl = 1;          // programmatic dependent launch along the tensor-core chain
+  int opt_front_variant = 0;  // diagnostic build only (tools/front_dbg.cu)
 };
 
 void spn_set_error(const char* fmt, ...);
@@ -110,10 +116,10 @@ struct SpnProfScope {
 
 // Launch with programmatic stream serialization: the kernel may begin (prologue: barriers, TMEM, weights) while the
 // previous kernel of the stream drains; it must execute griddepcontrol.wait before touching anything that kernel
-// wrote or read.  SPN_NO_PDL=1 falls back to a plain launch.
+// wrote or read.  pdl == false (spn_set_option "pdl" 0) falls back to a plain launch.
 template <typename... KArgs, typename... Args>
-inline cudaError_t spn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t dyn, cudaStream_t s, Args&&... args) {
-  static const bool off = getenv("SPN_NO_PDL") && atoi(getenv("SPN_NO_PDL")) != 0;
+inline cudaError_t spn_launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t dyn, cudaStream_t s, Args&&... args) {
+  const bool off = !pdl;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;

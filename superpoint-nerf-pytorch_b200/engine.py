@@ -9,10 +9,14 @@ Same YAML schema as the reference (``data``, ``homography_adaptation``, ``model`
   * the data loaders (COCO / HPatches image decoding) are out of scope: if the reference
     package is importable its ``get_loader`` is used, otherwise ``--synthetic N`` feeds N synthetic images of the
     configured size;
-  * ``train`` and ``export_NeRF_labels`` are out of scope and rejected.
+  * ``train`` and ``export_NeRF_labels`` are out of scope: their flags (``--training.*``) parse exactly as in the
+    reference, the task itself is rejected at dispatch;
+  * under ``torchrun`` (WORLD_SIZE > 1) every rank selects ``cuda:LOCAL_RANK``, joins the NCCL process group and takes
+    the dataset items with index = rank (mod world): no two ranks write the same file.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from pathlib import Path
 from typing import Literal
@@ -28,6 +32,23 @@ from .utils.sharding import shard_indices
 
 
 @dataclass
+class options:
+    """Training options (engine.py:14-28 of the reference; parsed for command-line compatibility, training itself is
+    outside this package).
+
+    Args:
+        validate_training: Validate during training.
+        include_mask_loss: Apply mask or no mask during loss (Do not include bordering artifacts by applying mask).
+        nerf_loss: Whether to use Descriptor NeRF loss or normal SuperPoint Descriptor loss.
+        train_nerf: Whether to enable training of NeRF datasets (Multiple datasets can be used for training)
+    """
+    validate_training: bool = False
+    include_mask_loss: bool = True
+    nerf_loss: bool = False
+    train_nerf: bool = False
+
+
+@dataclass
 class export_pseudo_labels_split:
     """Export pseudo labels on train, validation or test split.
 
@@ -37,6 +58,38 @@ class export_pseudo_labels_split:
     """
     enable_Homography_Adaptation: bool = True
     split: Literal["training", "validation", "test"] = "training"
+
+
+class ShardedLoader:
+    """Rank-strided view of any loader that yields one item per batch: item i goes to rank i % world.  Used for the
+    reference's DataLoaders under torchrun (a DataLoader cannot be re-sharded after construction); items of other ranks
+    are skipped after loading, which costs host time only."""
+
+    def __init__(self, loader, rank, world):
+        self.loader, self.rank, self.world = loader, rank, world
+
+    def __len__(self):
+        n = len(self.loader)
+        return (n - self.rank + self.world - 1) // self.world
+
+    def __iter__(self):
+        for i, item in enumerate(self.loader):
+            if i % self.world == self.rank:
+                yield item
+
+
+def init_distributed():
+    """-> (rank, world, device).  One process per GPU: cuda:LOCAL_RANK; NCCL group when WORLD_SIZE > 1."""
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        if local >= torch.cuda.device_count():
+            raise SystemExit(f"LOCAL_RANK {local} but only {torch.cuda.device_count()} CUDA devices are visible")
+        torch.cuda.set_device(local)
+        if not torch.distributed.is_initialized():
+            torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, f"cuda:{torch.cuda.current_device()}"
 
 
 class SyntheticLoader:
@@ -77,6 +130,7 @@ def load_pretrained(model, config, device):
 def main(config_path: str,
          task: Literal["export_pseudo_labels", "export_HPatches_Repeatability", "export_HPatches_Descriptors",
                        "train", "export_NeRF_labels"],
+         training: options = options(),
          pseudo_labels: export_pseudo_labels_split = export_pseudo_labels_split(),
          synthetic: int = 0, random_init: bool = False) -> None:
     """Run one export task.
@@ -93,10 +147,7 @@ def main(config_path: str,
         config = yaml.safe_load(f)
     if not torch.cuda.is_available():
         raise SystemExit("CUDA is not available: this implementation has no CPU fallback")
-    rank, world = 0, 1
-    if torch.distributed.is_available() and torch.distributed.is_initialized():
-        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-    device = f"cuda:{torch.cuda.current_device()}"
+    rank, world, device = init_distributed()
     model = get_model(config["model"], device=device)
     if not random_init:
         assert config["pretrained"], "Use pretrained model to export."
@@ -111,12 +162,19 @@ def main(config_path: str,
                              f"loading or pass --synthetic N ({e})")
         loader = get_loader(config, task, device="cpu", export_split=pseudo_labels.split) if task == "export_pseudo_labels" \
             else get_loader(config, task, device="cpu")
+        if world > 1:
+            loader = ShardedLoader(loader, rank, world)
     if task == "export_pseudo_labels":
+        if world > 1:   # device-sampler key = global dataset index: rank-strided items, see ExportDetections
+            config.setdefault("homography_adaptation", {}).update(index_stride=world, index_offset=rank)
         ExportDetections(config, model, loader, pseudo_labels.split, pseudo_labels.enable_Homography_Adaptation, device)
     elif task == "export_HPatches_Repeatability":
         Export_Hpatches_Repeatability(config, model, loader, device)
     else:
         Export_Hpatches_Descriptors(config, model, loader, device)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -51,6 +51,7 @@ class HomographyAdaptation:
         self.max_forwards = int(self.ha.get("max_forwards", 128))
         self.seed = int(self.ha.get("seed", 0))
         self.n_streams = max(1, int(self.ha.get("streams", 1)))
+        self.index_stride = max(1, int(self.ha.get("index_stride", 1)))   # rank sharding: image k of a group has index first + k*stride
         self._streams = None
         if not self.ha["valid_border_margin"]:
             # the reference's margin-0 path is shape-broken (mask stays 4-D)
@@ -62,7 +63,12 @@ class HomographyAdaptation:
         if self.ha.get("sampler", "device") == "numpy":
             hs = [self.sampler.sample_homography_host((H, W), **self.ha["params"]) for _ in range(NI * n_h)]
             return torch.cat(hs).view(NI, n_h, 3, 3).contiguous()
-        h, _ = self.sampler.sample_homographies_device((H, W), NI * n_h, seed=self.seed, first_index=first_index * n_h)
+        if self.index_stride == 1 or NI == 1:
+            h, _ = self.sampler.sample_homographies_device((H, W), NI * n_h, seed=self.seed, first_index=first_index * n_h)
+        else:
+            h = torch.cat([self.sampler.sample_homographies_device((H, W), n_h, seed=self.seed,
+                                                                   first_index=(first_index + k * self.index_stride) * n_h)[0]
+                           for k in range(NI)])
         return h.view(NI, n_h, 3, 3)
 
     def _sampling_matrices(self, ctx, homographies, NI, n_h, H, W, dev):
@@ -95,7 +101,7 @@ class HomographyAdaptation:
             lo, hi = int(idx[0]), int(idx[-1]) + 1
             with torch.cuda.stream(st):
                 hg = None if homographies is None else homographies[lo:hi]
-                heat, h = self._heatmaps_group(images[lo:hi], hg, enable_HA, first_index + lo, k)
+                heat, h = self._heatmaps_group(images[lo:hi], hg, enable_HA, first_index + lo * self.index_stride, k)
             heat.record_stream(cur)
             h.record_stream(cur)
             heats.append(heat)
@@ -228,24 +234,28 @@ class ExportDetections:
     @torch.no_grad()
     def homography_adaptation(self):
         """Same loop as export.py:82-129, software-pipelined: while the GPU works on group k the host saves group k-1."""
-        per_launch = int(self.config["homography_adaptation"].get("images_per_launch", 1))
-        group, done, pending = [], 0, None
+        ha = self.config["homography_adaptation"]
+        per_launch = int(ha.get("images_per_launch", 1))
+        # device-sampler key of an image = its index in the dataset order (x stride + offset under rank sharding), so
+        # the homographies of an image do not depend on which files already existed, on batching or on the rank
+        stride, offset = int(ha.get("index_stride", 1)), int(ha.get("index_offset", 0))
+        group, pending = [], None
 
         def flush():
-            nonlocal group, done, pending
+            nonlocal group, pending
             if not group:
                 return
-            cur = self._launch(group, done)
+            cur = self._launch(group, group[0][2])
             if pending is not None:
                 self._finish(pending)
             pending = cur
-            done += len(group)
             group = []
 
-        for data in tqdm(self.dataloader, desc="Exporting detections", colour="green"):
+        for seen, data in enumerate(tqdm(self.dataloader, desc="Exporting detections", colour="green")):
             name = data["name"][0]
             save_path = Path(self.output_dir, f"{name}.npy")
             if save_path.exists():                     # resume by file existence (export.py:89-91)
+                flush()                                # keeps the indices of a group consecutive
                 continue
             image = data["raw"]["image"]              # moved to the device per group (see _stage), not per image
             if not torch.is_tensor(image) or image.dim() != 4 or image.shape[0] != 1:
@@ -254,7 +264,7 @@ class ExportDetections:
                 image = image.float()
             if group and group[0][1].shape != image.shape:
                 flush()
-            group.append((save_path, image))
+            group.append((save_path, image, seen * stride + offset))
             if len(group) >= per_launch:
                 flush()
         flush()

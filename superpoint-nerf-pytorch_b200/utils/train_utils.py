@@ -1,5 +1,5 @@
 """Host-side helpers shared by the task classes."""
-from collections.abc import Mapping, Sequence
+from collections.abc import Mapping
 
 import torch
 
@@ -14,12 +14,18 @@ def move_to_device(batch, device, non_blocking=False):
         if isinstance(node, torch.Tensor):
             return node.to(device, non_blocking=non_blocking)
         if isinstance(node, Mapping):
-            return type(node)((key, walk(value)) for key, value in node.items())
+            pairs = [(key, walk(value)) for key, value in node.items()]
+            try:
+                return type(node)(pairs)
+            except TypeError:                       # e.g. defaultdict(factory): constructor does not take pairs
+                return dict(pairs)
         if isinstance(node, (str, bytes)):
             return node
-        if isinstance(node, Sequence):
+        if isinstance(node, tuple) and hasattr(node, "_fields"):     # namedtuple: positional constructor
+            return type(node)(*(walk(value) for value in node))
+        if isinstance(node, (list, tuple)):
             items = [walk(value) for value in node]
             return items if isinstance(node, list) else type(node)(items)
-        return node
+        return node                                 # range, arrays, scalars, anything else: unchanged
 
     return walk(batch)

@@ -277,6 +277,48 @@ def test_device_sampler_statistics(ctx):
     assert torch.equal(h2.cpu().double(), h[100:110])
 
 
+def _homography_features(m):
+    m = m / m[:, 2:3, 2:3]
+    ang = torch.atan2(m[:, 1, 0], m[:, 0, 0])
+    sc = torch.sqrt(m[:, 0, 0] ** 2 + m[:, 1, 0] ** 2)
+    c = m @ torch.tensor([160.0, 120.0, 1.0], dtype=torch.float64)
+    return torch.stack([ang, sc, c[:, 0] / c[:, 2], c[:, 1] / c[:, 2], m[:, 2, 0] * 1e3, m[:, 2, 1] * 1e3], 1).numpy()
+
+
+@pytest.mark.parametrize("tag,params", [
+    ("export_yaml", HA_CFG["params"]),                                                    # allow_artifacts=True (magicpoint_coco_export.yaml)
+    ("no_artifacts", dict(HA_CFG["params"], allow_artifacts=False, patch_ratio=0.5)),     # validity-filtered scale / angle candidates
+    ("no_artifacts_wide", dict(HA_CFG["params"], allow_artifacts=False, patch_ratio=0.7, scaling_amplitude=0.3, max_angle=0.8,
+                               n_angles=9, n_scales=3))])
+def test_device_sampler_distribution_ks(ctx, tag, params):
+    """Device sampler vs the reference's numpy sampler: two-sample Kolmogorov-Smirnov on six functionals of the matrices
+    (n = m = 2000, alpha = 1e-3 per functional), for allow_artifacts on and off (the off branch filters the scale and
+    angle candidates by validity, homographic_augmentation.py:61-66,90-95)."""
+    from scipy.stats import ks_2samp
+    n = 2000
+    H, W = 240, 320
+    h, hinv = ctx.sample_homographies(params, seed=17, first_index=0, count=n, H=H, W=W)
+    h = h.cpu().double()
+    np.random.seed(123)
+    ref = torch.cat([O.sample_homography((H, W), **params) for _ in range(n)]).double()
+    a, b = _homography_features(h), _homography_features(ref)
+    crit = 1.95 * np.sqrt(2.0 / n)                       # KS critical value at alpha = 0.001
+    for k in range(a.shape[1]):
+        st = ks_2samp(a[:, k], b[:, k]).statistic
+        assert st < crit, (tag, k, st, crit)
+    if not params["allow_artifacts"]:
+        # property of the filtered branch: the warped patch stays inside the image.  H = inverse(M), M: pts1 -> pts2
+        pr = params["patch_ratio"]
+        mg = (1 - pr) / 2
+        p1 = torch.tensor([[mg, mg], [mg, mg + pr], [mg + pr, mg + pr], [mg + pr, mg]], dtype=torch.float64) * torch.tensor([W, H])
+        p1h = torch.cat([p1, torch.ones(4, 1, dtype=torch.float64)], 1)
+        for mats in (h, ref):
+            q = torch.einsum("nij,kj->nki", torch.inverse(mats), p1h)
+            q = q[..., :2] / q[..., 2:]
+            assert float(q[..., 0].min()) > -1e-2 and float(q[..., 0].max()) < W + 1e-2
+            assert float(q[..., 1].min()) > -1e-2 and float(q[..., 1].max()) < H + 1e-2
+
+
 # ------------------------------------------------------------------------------------------------ end to end
 def test_ha_export_end_to_end_vs_golden(P, golden, tmp_path, monkeypatch):
     from superpoint_nerf_pytorch_b200 import settings

@@ -148,9 +148,9 @@ def test_fused_front_end_matches_unfused(monkeypatch):
         hinv = ctx.kornia_matrices(h, H, W)[0].view(NI, n_h, 3, 3)      # kornia sampling matrices of the warps
         warped, mask = ctx.warp_batch(imgs, hinv, 3)
         B = NI * (n_h + 1)
-        monkeypatch.setenv("SPN_TC_NOFUSE", "1")
+        ctx.set_option("fuse_front", 0)
         ref = m.prob_heatmap(warped, mask=mask).clone()
-        monkeypatch.setenv("SPN_TC_NOFUSE", "0")
+        ctx.set_option("fuse_front", 1)
         fused_plain = m.prob_heatmap(warped, mask=mask).clone()           # fused block_1+block_2, no warp
         fused_ha = m.prob_heatmap_ha(imgs, hinv, 0, B, mask=mask).clone()  # fused warp+block_1+block_2
         part = m.prob_heatmap_ha(imgs, hinv, 2, B - 3, mask=mask[2:B - 1]).clone()  # a slot sub-range
@@ -195,8 +195,8 @@ def test_fused_head_matches_unfused(monkeypatch):
         x = torch.from_numpy(np.stack([smooth_image(H, W, 30 + i) for i in range(B)])).cuda()
         mask = (torch.rand((B, H, W), device="cuda") > 0.2).to(torch.uint8)
         outs = {}
-        for tag, env in (("unfused", "1"), ("fused", "0")):
-            monkeypatch.setenv("SPN_TC_NOHEADFUSE", env)
+        for tag, env in (("unfused", 0), ("fused", 1)):
+            ctx.set_option("fuse_head", env)
             ctx.encoder_forward(x, m.mode)
             prob, logits = ctx.detector_head_forward(B, H, W, m.mode, mask=mask, want_logits=True)
             ctx.encoder_forward(x, m.mode)
@@ -217,9 +217,9 @@ def test_unfolded_conv_kernel_still_correct(sp_model, monkeypatch, name, shape):
     rng = np.random.RandomState(lid + 100)
     x = torch.from_numpy(np.maximum(rng.randn(*shape), 0).astype(np.float32))
     want = O.vgg_block(sd, name, x.half().float(), k, relu, pool).numpy()
-    monkeypatch.setenv("SPN_TC_FOLD", "0")
+    ctx.set_option("fold", 0)
     a = ctx.conv_layer(lid, x.cuda(), 1, relu=relu, pool=pool, cout=cout).cpu().numpy()
-    monkeypatch.setenv("SPN_TC_FOLD", "1")
+    ctx.set_option("fold", 1)
     b = ctx.conv_layer(lid, x.cuda(), 1, relu=relu, pool=pool, cout=cout).cpu().numpy()
     assert rel_err(a, want) < FAST and rel_err(b, want) < FAST
     assert rel_err(a, b) < 2e-3      # same operands, different summation order + one fp16 rounding

@@ -15,7 +15,7 @@ hinv = ctx.kornia_matrices(h, H, W)[0].view(1, NH, 3, 3)
 names = {0: "baseline", 3: "P: nothing", 12: "E1: nothing", 16: "E2: no stores", 32: "E2: no ALU/stores", 96: "E2: nothing",
          128: "M: 4 of 36 MMA2", 111: "only MMAs", 15: "P+E1 off", 108: "E1+E2 off", 99: "P+E2 off", 0.5: "baseline again"}
 for dbg, name in names.items():
-    os.environ["SPN_FRONT_DBG"] = str(int(dbg))
+    ctx.set_option("front_variant", int(dbg))
     for _ in range(2):
         ctx.encoder_forward_ha(imgs, hinv, 0, NH + 1, 1)
     torch.cuda.synchronize()
