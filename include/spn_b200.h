@@ -86,9 +86,11 @@ SPN_API int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, int 
 /* Fused K.warp_perspective(image, H) (export.py:51) + VGG_BACKBONE.forward for the homography-adaptation slots
  * slot = i*(n_h+1) + j (j == 0: image i itself, j >= 1: image i warped by homography j-1) with
  * slot_begin <= slot < slot_begin + n_slots; tensor-core modes only.  The warped images are never written to memory:
- * the warp is evaluated inside the first convolution kernel.  d_images [n_images][H][W], d_ainv [n_images][n_h][9]
- * (kornia sampling matrices, as for spn_warp_batch).  Leaves the feature map of the n_slots forwards inside ctx. */
-SPN_API int spn_encoder_forward_ha(spn_ctx* ctx, const float* d_images, int n_images, const float* d_ainv, int n_h,
+ * the warp is evaluated inside the first convolution kernel.  d_images [n_images][H][W], d_hinv [n_images][n_h][9] =
+ * the PIXEL-space inverses H_ij^-1 (export.py:49; kornia samples the source at H^-1 p).  The operands downstream are 16
+ * bits wide, so this entry point does not need kornia's bit-exact normalised chain; the validity masks that go with
+ * these forwards still come from spn_warp_batch.  Leaves the feature map of the n_slots forwards inside ctx. */
+SPN_API int spn_encoder_forward_ha(spn_ctx* ctx, const float* d_images, int n_images, const float* d_hinv, int n_h,
                                    int slot_begin, int n_slots, int H, int W, int mode, spn_stream stream);
 
 /* Detector_head.forward up to prob_heatmap (heads.py:17-28): convPa, convPb, softmax(65), drop dustbin,
@@ -111,6 +113,18 @@ SPN_API int spn_dense_descriptors(spn_ctx* ctx, const float* d_desc_raw, int B, 
 SPN_API int spn_sample_descriptors(spn_ctx* ctx, const float* d_desc_raw, int B, int C, int Hc, int Wc, int grid,
                            const int32_t* d_kp, const int32_t* d_kp_count, int max_kp, int interp, float* d_out,
                            spn_stream stream);
+
+/* SuperPoint.forward (models/SuperPoint.py:17-30) + the keypoint extraction every consumer performs on its output
+ * (nonzero(prob_heatmap_nms), desc[:, y, x]: evaluations/descriptor_evaluation.py:55-69) in ONE call: encoder, detector
+ * head, box_nms + top-k once, descriptor head, descriptors at the keypoints only (no dense 315 MB map).
+ * d_images [B][H][W]; outputs: d_logits [B][65][H/8][W/8] (nullable), d_prob [B][H][W], d_nms [B][H][W] (nullable),
+ * d_pred [B][H][W] int32 (nullable), d_kp [B][max_kp][2] int32 (row, col) row-major order, d_kp_count [B] (true count),
+ * d_desc_raw [B][256][H/8][W/8] and d_desc_sparse [B][max_kp][256] (both or neither; rows >= count are zero).
+ * interp: 0 = bicubic (the reference's dense desc evaluated at the keypoint), 1 = bilinear. */
+SPN_API int spn_detect_describe(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode, float nms_size, float iou,
+                                float det_thresh, int top_k, int interp, float* d_logits, float* d_prob, float* d_nms,
+                                int32_t* d_pred, int32_t* d_kp, int32_t* d_kp_count, int max_kp, float* d_desc_raw,
+                                float* d_desc_sparse, spn_stream stream);
 
 /* box_nms (sp_utils.py:4-28) + threshold (heads.py:41 / export.py:123) + nonzero (export.py:125), batched.
  * d_prob [B][H][W]; outputs (each nullable): d_nms [B][H][W] fp32, d_pred [B][H][W] int32 (= nms >= det_thresh),

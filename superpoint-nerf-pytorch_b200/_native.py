@@ -49,6 +49,7 @@ PROTOTYPES = {
     "spn_descriptor_head_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "spn_dense_descriptors": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "spn_sample_descriptors": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "spn_detect_describe": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "spn_box_nms_topk": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "spn_nms_stats": (_i, [_vp, _i, _i, _i, _vp]),
     "spn_warp_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -249,9 +250,34 @@ class Context:
         _chk_dev(kp_count, torch.int32, "kp_count", self.device)
         B, Cc, Hc, Wc = raw.shape
         max_kp = kp.shape[1]
-        out = torch.zeros((B, max_kp, Cc), dtype=torch.float32, device=raw.device)
+        out = torch.empty((B, max_kp, Cc), dtype=torch.float32, device=raw.device)   # the kernel zeroes rows >= count
         self._call("spn_sample_descriptors", self.handle, _ptr(raw), B, Cc, Hc, Wc, grid, _ptr(kp), _ptr(kp_count), max_kp,
                    0 if interp == "bicubic" else 1, _ptr(out), self._s())
+        return out
+
+    def detect_describe(self, images, mode, nms_size, det_thresh, top_k=0, iou=0.1, max_kp=None, descriptors=True,
+                        interp="bicubic", want_logits=True, want_map=True, want_pred=True):
+        """One-call forward + keypoints (+ sparse descriptors): images (B,H,W) fp32 CUDA -> dict with logits, prob, nms,
+        pred, kp (B,max_kp,2) int32 (row, col), kp_count (B,), desc_raw, desc_sparse (B,max_kp,256)."""
+        images = _dense(images)
+        _chk_dev(images, torch.float32, "images", self.device)
+        B, H, W = images.shape
+        dev = images.device
+        if max_kp is None:
+            max_kp = int(top_k) if top_k else min(H * W, 16384)
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = {"logits": torch.empty((B, 65, H // 8, W // 8), **f32) if want_logits else None,
+               "prob": torch.empty((B, H, W), **f32),
+               "nms": torch.empty((B, H, W), **f32) if want_map else None,
+               "pred": torch.empty((B, H, W), dtype=torch.int32, device=dev) if want_pred else None,
+               "kp": torch.empty((B, max_kp, 2), dtype=torch.int32, device=dev),
+               "kp_count": torch.empty((B,), dtype=torch.int32, device=dev),
+               "desc_raw": torch.empty((B, 256, H // 8, W // 8), **f32) if descriptors else None,
+               "desc_sparse": torch.empty((B, max_kp, 256), **f32) if descriptors else None}
+        self._call("spn_detect_describe", self.handle, _ptr(images), B, H, W, mode, C.c_float(nms_size), C.c_float(iou),
+                   C.c_float(det_thresh), int(top_k), 0 if interp == "bicubic" else 1, _ptr(out["logits"]), _ptr(out["prob"]),
+                   _ptr(out["nms"]), _ptr(out["pred"]), _ptr(out["kp"]), _ptr(out["kp_count"]), int(max_kp), _ptr(out["desc_raw"]),
+                   _ptr(out["desc_sparse"]), self._s())
         return out
 
     def box_nms(self, prob, size, iou=0.1, min_prob=0.01, top_k=0, det_thresh=None, want_map=True, want_pred=False,

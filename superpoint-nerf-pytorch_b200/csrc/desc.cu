@@ -151,7 +151,11 @@ sparse_desc_kernel(const float* __restrict__ raw, int C, int Hc, int Wc, int gri
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int n = min(__ldg(&kp_count[b]), max_kp);
-  if (k >= n) return;
+  if (k >= max_kp) return;
+  if (k >= n) {  // slots beyond the keypoint count are zero
+    for (int c = lane; c < C; c += 32) out[((size_t)b * max_kp + k) * C + c] = 0.f;
+    return;
+  }
   const int y = __ldg(&kp[((size_t)b * max_kp + k) * 2]), x = __ldg(&kp[((size_t)b * max_kp + k) * 2 + 1]);
   const Taps t = make_taps(y, x, Hc, Wc, 1.0f / (float)grid, bicubic != 0);
   const float* rb = raw + (size_t)b * C * Hc * Wc;

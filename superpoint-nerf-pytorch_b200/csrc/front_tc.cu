@@ -46,7 +46,7 @@ constexpr int kPThreads = 256;                        // P role: warps 10-17
 
 struct FrontParams {
   const float* images;   // [n_src][H][W] fp32
-  const float* hinv;     // [n_src][n_h][9] normalised kornia sampling matrices, or null (plain forward: slot == source image)
+  const float* hinv;     // [n_src][n_h][9] pixel-space H^-1, or null (plain forward: slot == source image)
   int n_h;               // homographies per source image (slot = src * (n_h + 1) + j, j == 0 is the identity)
   int slot_begin, n_slots;
   int H, W, tiles_x, tiles_y;
@@ -209,10 +209,8 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       mbar_wait(&bar_a1_empty[b], ph ^ 1u);  // MMA1 of tile i-3 has consumed A1[b] (and patch_s[b] long before)
       if (j > 0 && slot != hm_slot) {  // warp-uniform; a CTA's consecutive tiles mostly belong to the same slot
         const float* hp = p.hinv + ((size_t)src * p.n_h + (j - 1)) * 9;
-        float a[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) a[k] = __ldg(hp + k);
-        kornia_to_pixel(a, p.H, p.W, hm);  // normalised kornia sampling matrix -> pixel space (16-bit operands downstream)
+        for (int k = 0; k < 9; ++k) hm[k] = __ldg(hp + k);
         hm_slot = slot;
       }
       // 1. the 12 x 20 patch of the warped image around the tile (zero outside the frame = block_1's padding)

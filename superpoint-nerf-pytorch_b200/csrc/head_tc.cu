@@ -8,8 +8,11 @@
 // GEMM view: M = 128 cells (8 wide x 16 high, TMEM lane = cell), N = 80 (65 padded to the next legal UMMA N for M = 128),
 // K = 256 = 4 channel blocks x 4 K-steps.  One epilogue thread owns one cell: it reads the 65 fp32 logits from TMEM,
 // computes exp(l - max) / sum exactly like softmax_d2s_kernel, and writes the cell's 8 x 8 block of the heatmap
-// (times the mask) with float4 stores.  Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer,
-// warps 2-5 epilogue; bias through one extra MMA against a constant ones operand.
+// (times the mask) with float4 stores.  Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 and 6-9 two
+// epilogue groups that alternate tiles (one per TMEM accumulator), so one group's exp / store phase overlaps the
+// other's TMEM reads; the mask bytes of a cell are fetched before the accumulator wait (they do not depend on the
+// MMAs), which takes their DRAM latency off the per-row store loop.  Bias through one extra MMA against a constant
+// ones operand.
 #include <cuda.h>
 #include <math.h>
 
@@ -30,15 +33,15 @@ constexpr uint32_t kChStride = (uint32_t)kTH * kTW * 16;   // 2048 B between 8-c
 constexpr int kSlabBytes = 8 * kTH * kTW * 16;      // 16384 B: 64 channels of 128 cells
 constexpr int kOnesBytes = 4096;
 constexpr int kStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA, MMA, 2 x 4 epilogue warps
 
 struct HeadParams {
   int n_img, Hc, Wc, tiles_x, tiles_y;
   int is_bf16;
   const void* wimg;
-  const uint8_t* mask;   // [n][H][W] or null
-  float* logits;         // [n][65][Hc][Wc] or null
-  float* prob;           // [n][H][W]
+  const uint8_t* __restrict__ mask;   // [n][H][W] or null
+  float* __restrict__ logits;         // [n][65][Hc][Wc] or null
+  float* __restrict__ prob;           // [n][H][W]
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -135,28 +138,35 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadParams p) {
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue: one thread = one 8x8 cell =====================
-    const int q = warp & 3;
+    // ===================== epilogue: one thread = one 8x8 cell; group = accumulator =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;        // 0: warps 2-5, 1: warps 6-9
     const int g = q * 4 + (lane >> 3), r = lane & 7;
     const int H = p.Hc * 8, W = p.Wc * 8;
     const size_t cells = (size_t)p.Hc * p.Wc;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    int i = grp;
+    for (int t = blockIdx.x + grp * gridDim.x; t < n_tiles; t += 2 * gridDim.x, i += 2) {
+      const uint32_t acc_phase = (uint32_t)(i >> 1) & 1u;
       const int n = t / tiles_per_img, rr = t - n * tiles_per_img;
       const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
       const int cy = ty * kTH + g, cx = tx * kTW + r;
-      mbar_wait(&bar_tfull[acc], acc_phase);
+      const bool live = cy < p.Hc && cx < p.Wc;
+      const size_t o0 = ((size_t)n * H + cy * 8) * W + cx * 8;
+      uint2 mm[8];
+      if (p.mask && live) {
+#pragma unroll
+        for (int dy = 0; dy < 8; ++dy) mm[dy] = __ldg(reinterpret_cast<const uint2*>(p.mask + o0 + (size_t)dy * W));
+      }
+      mbar_wait(&bar_tfull[grp], acc_phase);
       tc_fence_after();
       uint32_t v[80];
-      const uint32_t taddr = tmem_base + (uint32_t)acc * 128 + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)grp * 128 + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c0 = 0; c0 < 80; c0 += 16) tmem_ld16(taddr + c0, v + c0);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bar_tempty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (cy >= p.Hc || cx >= p.Wc) continue;
+      mbar_arrive(&bar_tempty[grp]);
+      if (!live) continue;
       if (p.logits) {
         float* lp = p.logits + (size_t)n * 65 * cells + (size_t)cy * p.Wc + cx;
 #pragma unroll
@@ -176,16 +186,15 @@ head_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadParams p) {
       const float inv_s = 1.0f / s;
 #pragma unroll
       for (int dy = 0; dy < 8; ++dy) {
-        const size_t o = ((size_t)n * H + cy * 8 + dy) * W + cx * 8;
+        const size_t o = o0 + (size_t)dy * W;
         float pr[8];
 #pragma unroll
         for (int dx = 0; dx < 8; ++dx) pr[dx] = __uint_as_float(v[dy * 8 + dx]) * inv_s;
         if (p.mask) {
-          const uint2 mm = *reinterpret_cast<const uint2*>(p.mask + o);
 #pragma unroll
           for (int dx = 0; dx < 4; ++dx) {
-            pr[dx] *= (float)((mm.x >> (8 * dx)) & 0xff);
-            pr[4 + dx] *= (float)((mm.y >> (8 * dx)) & 0xff);
+            pr[dx] *= (float)((mm[dy].x >> (8 * dx)) & 0xff);
+            pr[4 + dx] *= (float)((mm[dy].y >> (8 * dx)) & 0xff);
           }
         }
         *reinterpret_cast<float4*>(p.prob + o) = make_float4(pr[0], pr[1], pr[2], pr[3]);

@@ -303,3 +303,29 @@ extern "C" int spn_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_
   SPN_REQUIRE(mode == SPN_MODE_F16 || mode == SPN_MODE_BF16, "spn_conv_layer: unknown mode %d", mode);
   return spn_tc_conv_layer(ctx, layer, mode, d_in, B, H, W, relu != 0, pool != 0, d_out, s);
 }
+
+// SuperPoint.forward + keypoint extraction in ONE call (models/SuperPoint.py:17-30 followed by what every consumer does
+// with the output: nonzero(prob_heatmap_nms) and desc[:, y, x], evaluations/descriptor_evaluation.py:55-69): encoder,
+// detector head, box_nms + top-k ONCE (map, pred and the row-major keypoint list from the same pass), descriptor head,
+// descriptors evaluated only at the keypoints.  Everything is enqueued back to back on `stream` from one host call.
+extern "C" int spn_detect_describe(spn_ctx* ctx, const float* d_images, int B, int H, int W, int mode, float nms_size, float iou,
+                                   float det_thresh, int top_k, int interp, float* d_logits, float* d_prob, float* d_nms,
+                                   int32_t* d_pred, int32_t* d_kp, int32_t* d_kp_count, int max_kp, float* d_desc_raw,
+                                   float* d_desc_sparse, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_images && d_prob && d_kp && d_kp_count && max_kp > 0, "spn_detect_describe: null pointer / max_kp");
+  SPN_REQUIRE((d_desc_raw != nullptr) == (d_desc_sparse != nullptr), "spn_detect_describe: d_desc_raw and d_desc_sparse go together");
+  int rc = spn_encoder_forward(ctx, d_images, B, H, W, mode, stream);
+  if (rc) return rc;
+  if ((rc = spn_detector_head_forward(ctx, B, H, W, mode, nullptr, d_logits, d_prob, stream))) return rc;
+  if (d_desc_raw && (rc = spn_descriptor_head_forward(ctx, B, H, W, mode, d_desc_raw, stream))) return rc;
+  if (nms_size > 0.f) {
+    if ((rc = spn_box_nms_topk(ctx, d_prob, B, H, W, nms_size, iou, det_thresh, top_k, det_thresh, d_nms, d_pred, d_kp, d_kp_count,
+                               max_kp, stream))) return rc;
+  } else {
+    spn_set_error("spn_detect_describe: nms_size must be > 0 (the keypoint list comes from the NMS pass)");
+    return SPN_E_INVALID;
+  }
+  if (d_desc_raw)
+    return spn_sample_descriptors(ctx, d_desc_raw, B, 256, H / 8, W / 8, 8, d_kp, d_kp_count, max_kp, interp, d_desc_sparse, stream);
+  return SPN_OK;
+}

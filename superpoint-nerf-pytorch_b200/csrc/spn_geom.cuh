@@ -126,25 +126,6 @@ __device__ __forceinline__ float bilinear_zero_exact(const float* __restrict__ i
   return bilinear_combine(nwv, nev, swv, sev, sx, sy, fx, fy);
 }
 
-// Pixel-space matrix equivalent to a normalised kornia sampling matrix (for the fused 16-bit front end, where the
-// last bits of the coordinate do not matter): p_src = m . (x, y, 1) up to the homogeneous divide.
-__device__ __forceinline__ void kornia_to_pixel(const float* __restrict__ a, int H, int W, float* __restrict__ m) {
-  const double sxn = 2.0 / (double)(W - 1), syn = 2.0 / (double)(H - 1), hw = 0.5 * (W - 1), hh = 0.5 * (H - 1);
-  double r[3][3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    r[k][0] = (double)a[3 * k] * sxn;
-    r[k][1] = (double)a[3 * k + 1] * syn;
-    r[k][2] = (double)a[3 * k + 2] - (double)a[3 * k] - (double)a[3 * k + 1];
-  }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    m[c] = (float)(hw * (r[0][c] + r[2][c]));
-    m[3 + c] = (float)(hh * (r[1][c] + r[2][c]));
-    m[6 + c] = (float)r[2][c];
-  }
-}
-
 // Exact t / d for 0 <= t, t * d < 2^40, with m = ceil(2^40 / d) computed on the host (fast_div_magic).
 __device__ __forceinline__ int fast_div(int t, unsigned long long m) {
   return (int)(((unsigned long long)(unsigned)t * m) >> 40);

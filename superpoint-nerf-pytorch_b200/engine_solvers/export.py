@@ -72,13 +72,15 @@ class HomographyAdaptation:
         return h.view(NI, n_h, 3, 3)
 
     def _sampling_matrices(self, ctx, homographies, NI, n_h, H, W, dev):
-        """-> (h on the device, fwd, bwd): kornia's normalised sampling matrices for H and H^-1 (export.py:49-55,72)."""
+        """-> (h, h_inv, fwd, bwd) on the device: H, its pixel-space inverse (export.py:49) and kornia's normalised
+        sampling matrices for H and H^-1 (the grids of the warps at export.py:51-55,72)."""
         if homographies.is_cuda and self.ha.get("geometry", "auto") != "host":
             h = homographies.to(dev, torch.float32).contiguous().view(NI, n_h, 3, 3)
             fwd, bwd = ctx.kornia_matrices(h, H, W)
-            return h, fwd, bwd
-        fwd, bwd = sampling_matrices(homographies, (H, W))           # the reference's torch calls on the host
-        pack = torch.stack([homographies.detach().to("cpu", torch.float32).reshape(-1, 3, 3), fwd, bwd]).to(dev)
+            return h, ctx.invert3x3(h), fwd, bwd
+        hc = homographies.detach().to("cpu", torch.float32).reshape(-1, 3, 3)
+        fwd, bwd = sampling_matrices(hc, (H, W))                      # the reference's torch calls on the host
+        pack = torch.stack([hc, torch.inverse(hc), fwd, bwd]).to(dev)
         return tuple(t.view(NI, n_h, 3, 3) for t in pack)
 
     @torch.no_grad()
@@ -121,9 +123,9 @@ class HomographyAdaptation:
             return self.model.prob_heatmap(imgs, slot=slot), None
         if homographies is None:
             homographies = self._homographies(NI, n_h, H, W, first_index)
-        h, hinv, hback = self._sampling_matrices(ctx, homographies, NI, n_h, H, W, imgs.device)   # export.py:49 + kornia
+        h, hinv, fwd, hback = self._sampling_matrices(ctx, homographies, NI, n_h, H, W, imgs.device)   # export.py:49 + kornia
         fused = self.model.mode != 0 and self.ha.get("fused_warp", True)         # tensor-core modes: warp inside conv kernel
-        warped, mask = ctx.warp_batch(imgs, hinv, self.ha["valid_border_margin"], want_warped=not fused)  # export.py:51-66
+        warped, mask = ctx.warp_batch(imgs, fwd, self.ha["valid_border_margin"], want_warped=not fused)  # export.py:51-66
         B = NI * (n_h + 1)
         probs = torch.empty((B, H, W), dtype=torch.float32, device=imgs.device)
         for s in range(0, B, self.max_forwards):                                 # export.py:69-70

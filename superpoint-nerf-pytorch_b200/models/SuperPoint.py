@@ -6,7 +6,11 @@ The nn.Conv2d / nn.BatchNorm2d sub-modules only *hold* the parameters (so ``stat
 Inference only (the reference's export tasks call ``model.eval()``, export.py:21): BN uses running stats.
 
 Extension keys (all optional) in the ``model`` config: ``precision`` in {'fp32','f16','bf16'} (default from
-$SPN_B200_PRECISION, else 'fp32'), ``dense_desc`` (default True, as the reference).
+$SPN_B200_PRECISION, else 'fp32'), ``dense_desc`` (default True, as the reference), ``keypoints`` (default False): add
+``detector_output['keypoints']`` (B,max_kp,2) int32 (row, col; row-major order like torch.nonzero of prob_heatmap_nms),
+``detector_output['keypoint_count']`` (B,) and ``descriptor_output['desc_sparse']`` (B,max_kp,256) = desc[:, y, x] at the
+keypoints - computed by ONE C-ABI call (spn_detect_describe: NMS once, no dense 315 MB descriptor map unless
+``dense_desc`` is also set).  ``forward(x, keypoints=True)`` does the same per call.
 """
 import itertools
 import os
@@ -104,7 +108,7 @@ class SuperPoint(nn.Module):
 
     # ---- forward (models/SuperPoint.py:17-30) ----------------------------------------------------
     @torch.no_grad()
-    def forward(self, x, mask=None):
+    def forward(self, x, mask=None, keypoints=None):
         if not (torch.is_tensor(x) and x.is_cuda):
             raise NativeError("input must be a CUDA tensor (no CPU fallback)")
         if x.dim() != 4 or x.shape[1] != 1:
@@ -112,6 +116,10 @@ class SuperPoint(nn.Module):
         B, _, H, W = x.shape
         ctx = self.native()
         dh = self.detector_head.config
+        if keypoints is None:
+            keypoints = bool(self.config.get("keypoints", False))
+        if keypoints and dh["nms"] and mask is None:
+            return self._forward_keypoints(ctx, x, B, H, W, dh)
         with torch.cuda.device(x.device):
             img = x.detach().to(torch.float32).contiguous().view(B, H, W)
             ctx.encoder_forward(img, self.mode)
@@ -130,6 +138,22 @@ class SuperPoint(nn.Module):
                 d = {"desc_raw": raw}
                 if self.config.get("dense_desc", True):
                     d["desc"] = ctx.dense_descriptors(raw, self.descriptor_head.config["grid_size"])
+                out["descriptor_output"] = d
+        return out
+
+    def _forward_keypoints(self, ctx, x, B, H, W, dh):
+        """forward + post-NMS keypoints (+ descriptors at the keypoints) through one spn_detect_describe call."""
+        sp = hasattr(self, "descriptor_head")
+        with torch.cuda.device(x.device):
+            img = x.detach().to(torch.float32).contiguous().view(B, H, W)
+            r = ctx.detect_describe(img, self.mode, float(dh["nms"]), float(dh["det_thresh"]), int(dh["top_k"]), descriptors=sp,
+                                    interp=self.config.get("desc_interp", "bicubic"))
+            out = {"detector_output": {"logits": r["logits"], "prob_heatmap": r["prob"], "prob_heatmap_nms": r["nms"],
+                                       "pred_pts": r["pred"], "keypoints": r["kp"], "keypoint_count": r["kp_count"]}}
+            if sp:
+                d = {"desc_raw": r["desc_raw"], "desc_sparse": r["desc_sparse"]}
+                if self.config.get("dense_desc", False):
+                    d["desc"] = ctx.dense_descriptors(r["desc_raw"], self.descriptor_head.config["grid_size"])
                 out["descriptor_output"] = d
         return out
 

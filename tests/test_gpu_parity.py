@@ -282,7 +282,11 @@ def _homography_features(m):
     ang = torch.atan2(m[:, 1, 0], m[:, 0, 0])
     sc = torch.sqrt(m[:, 0, 0] ** 2 + m[:, 1, 0] ** 2)
     c = m @ torch.tensor([160.0, 120.0, 1.0], dtype=torch.float64)
-    return torch.stack([ang, sc, c[:, 0] / c[:, 2], c[:, 1] / c[:, 2], m[:, 2, 0] * 1e3, m[:, 2, 1] * 1e3], 1).numpy()
+    f = torch.stack([ang, sc, c[:, 0] / c[:, 2], c[:, 1] / c[:, 2], m[:, 2, 0] * 1e3, m[:, 2, 1] * 1e3], 1).numpy()
+    # the perspective row is exactly 0 for unrotated draws (an atom of the distribution); it is realised as +-1e-7
+    # solver noise whose sign differs between implementations: collapse it so the KS test sees the atom, not the noise
+    f[:, 4:] = np.round(f[:, 4:], 3)
+    return f
 
 
 @pytest.mark.parametrize("tag,params", [
@@ -526,3 +530,32 @@ def test_preprocessing_kernel_vs_reference(ctx, golden):
     want = O.ratio_preserving_resize(big.to(torch.float32), (240, 320)).numpy()
     got = ratio_preserving_resize(big.cuda(), (240, 320)).cpu().numpy()
     assert np.abs(got - want).max() < 2e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "f16"])
+def test_forward_with_keypoints_one_call(P, golden, precision):
+    """forward(x, keypoints=True) = spn_detect_describe: the same maps as the plain forward, the keypoint list ==
+    nonzero(prob_heatmap_nms) in row-major order, desc_sparse == dense desc[:, y, x] at those keypoints (what
+    descriptor_evaluation.py:55-69 reads); in fp32 also against the reference's golden forward."""
+    g = golden("forward_superpoint.npz")
+    sd = O.make_state_dict("superpoint", seed=int(g["seed"]), logit_gain=float(g["gain"]))
+    m = make_model(dict(SP_MODEL, dense_desc=True), sd, precision)
+    x = torch.from_numpy(g["x"]).cuda()
+    plain = m(x)
+    kp_out = m(x, keypoints=True)
+    for k in ("logits", "prob_heatmap", "prob_heatmap_nms", "pred_pts"):
+        assert torch.equal(plain["detector_output"][k], kp_out["detector_output"][k]), k
+    assert torch.equal(plain["descriptor_output"]["desc_raw"], kp_out["descriptor_output"]["desc_raw"])
+    B = x.shape[0]
+    for b in range(B):
+        n = int(kp_out["detector_output"]["keypoint_count"][b])
+        kp = kp_out["detector_output"]["keypoints"][b, :n].cpu().numpy()
+        want = np.argwhere(plain["detector_output"]["prob_heatmap_nms"][b].cpu().numpy() >= SP_MODEL["detector_head"]["det_thresh"])
+        assert np.array_equal(kp, want) and 0 < n <= SP_MODEL["detector_head"]["top_k"]
+        dense = plain["descriptor_output"]["desc"][b].cpu().numpy()[:, kp[:, 0], kp[:, 1]].T
+        sparse = kp_out["descriptor_output"]["desc_sparse"][b].cpu().numpy()
+        assert rel_err(sparse[:n], dense) < STRICT
+        assert np.all(sparse[n:] == 0)
+    if precision == "fp32":
+        assert np.array_equal(kp_out["detector_output"]["pred_pts"].cpu().numpy(), g["pred_pts"]) or \
+            min(keypoint_agreement(np.argwhere(kp_out["detector_output"]["pred_pts"][0].cpu().numpy() > 0), np.argwhere(g["pred_pts"][0] > 0))) >= 0.99

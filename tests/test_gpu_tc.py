@@ -144,9 +144,10 @@ def test_fused_front_end_matches_unfused(monkeypatch):
     ctx = m.native()
     for (NI, H, W, n_h) in [(2, 240, 320, 3), (1, 120, 160, 5), (3, 40, 72, 2)]:
         imgs = torch.from_numpy(np.stack([smooth_image(H, W, 60 + i) for i in range(NI)])).cuda()
-        h, _ = ctx.sample_homographies(HA_CFG["params"], seed=3, first_index=0, count=NI * n_h, H=H, W=W)
-        hinv = ctx.kornia_matrices(h, H, W)[0].view(NI, n_h, 3, 3)      # kornia sampling matrices of the warps
-        warped, mask = ctx.warp_batch(imgs, hinv, 3)
+        h, hinv = ctx.sample_homographies(HA_CFG["params"], seed=3, first_index=0, count=NI * n_h, H=H, W=W)
+        hinv = hinv.view(NI, n_h, 3, 3)                                 # pixel-space inverses for the fused front end
+        fwd = ctx.kornia_matrices(h, H, W)[0].view(NI, n_h, 3, 3)       # kornia sampling matrices for warp_batch
+        warped, mask = ctx.warp_batch(imgs, fwd, 3)
         B = NI * (n_h + 1)
         ctx.set_option("fuse_front", 0)
         ref = m.prob_heatmap(warped, mask=mask).clone()

@@ -71,12 +71,10 @@ def main():
         m = get_model(dict(copy.deepcopy(SP), precision=prec), "cuda").eval()
         ctx = m.native()
 
-        def fwd_sparse():
-            o = m(x3)
-            r = ctx.box_nms(o["detector_output"]["prob_heatmap"], 4.0, 0.1, 0.001, 1000, det_thresh=0.001, want_map=False, max_kp=1024)
-            return ctx.sample_descriptors(o["descriptor_output"]["desc_raw"], 8, r["kp"], r["kp_count"])
+        def fwd_sparse():   # one C-ABI call: forward + NMS/top-k once + descriptors at the 1000 keypoints
+            return m(x3, keypoints=True)["descriptor_output"]["desc_sparse"]
 
-        ms = timed(fwd_sparse)
+        ms = timed(fwd_sparse, iters=50)
         d = fwd_sparse()
         out[f"config3_{prec}_sparse"] = {"ms_per_image": ms, "img_per_s": 1e3 / ms, "descriptors": list(d.shape)}
         md = get_model(dict(copy.deepcopy(SP), precision=prec, dense_desc=True), "cuda").eval()
@@ -102,6 +100,14 @@ def main():
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         out[f"config4_{H}x{W}"] = {"pairs_per_s": n / dt, "note": "includes D2H and np.savez_compressed of 5 arrays per pair"}
+    import subprocess
+    try:   # clock record for these builder-run numbers
+        q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.sw_power_cap,"
+                            "clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown", "--format=csv,noheader"],
+                           capture_output=True, text=True, timeout=10).stdout.strip()
+        out["clocks_after_run"] = q
+    except Exception as e:
+        out["clocks_after_run"] = f"unavailable: {e}"
     print(json.dumps(out, indent=1))
 
 

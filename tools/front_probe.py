@@ -10,7 +10,7 @@ ctx = model.native()
 H, W, NH = 240, 320, 99
 imgs = torch.rand((1, H, W), device=dev)
 h, hinv = ctx.sample_homographies(bench.HA_CFG["params"], 1, 0, NH, H, W)
-hinv = ctx.kornia_matrices(h, H, W)[0].view(1, NH, 3, 3)
+hinv = hinv.view(1, NH, 3, 3)
 # needs a library built with SPN_FRONT_DBG_BUILD=1 (extra template instantiations)
 names = {0: "baseline", 3: "P: nothing", 12: "E1: nothing", 16: "E2: no stores", 32: "E2: no ALU/stores", 96: "E2: nothing",
          128: "M: 4 of 36 MMA2", 111: "only MMAs", 15: "P+E1 off", 108: "E1+E2 off", 99: "P+E2 off", 0.5: "baseline again"}
