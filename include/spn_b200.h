@@ -196,6 +196,34 @@ SPN_API int spn_resize_crop(spn_ctx* ctx, const void* d_src, int src_is_u8, int 
 /* 3x3 inverse, fp32, batched (export.py:49 torch.inverse). d_in/d_out [count][9]. */
 SPN_API int spn_invert3x3(spn_ctx* ctx, const float* d_in, int count, float* d_out, spn_stream stream);
 
+/* ---- on-GPU evaluation of the exports (evaluations/detector_evaluation.py, evaluations/descriptor_evaluation.py) ---- */
+
+/* np.where(prob > 0) + warp_keypoints / keep_true_keypoints / filter_keypoints + select_k_best
+ * (detector_evaluation.py:152-206, descriptor_evaluation.py:17-52), per map.  d_prob [B][H][W] (an NMS'd heatmap);
+ * h_warp HOST double [B][9] (nullable): homography applied to (x = col, y = row, 1) in fp64 like numpy; a point is kept
+ * iff its warped position satisfies 0 <= row' < bound_h and 0 <= col' < bound_w.  emit_warped = 0 writes the original
+ * integer (row, col) (keep_true_keypoints), 1 writes the warped (row', col') (warp_keypoints + filter_keypoints).
+ * Output: the keep_k most probable points in ASCENDING order of probability (select_k_best): d_pts [B][keep_k][2] double,
+ * d_score [B][keep_k], d_count [2*B]: [b] = points written, [B + b] = candidates before the selection (at most 16384
+ * candidates per map are held on chip; a larger count means the result is truncated and the caller must fall back). */
+SPN_API int spn_select_keypoints(spn_ctx* ctx, const float* d_prob, int B, int H, int W, const double* h_warp, int bound_h,
+                                 int bound_w, int emit_warped, int keep_k, double* d_pts, float* d_score, int32_t* d_count,
+                                 spn_stream stream);
+
+/* Repeatability counts (detector_evaluation.py:214-233): d_pts1 / d_pts2 [B][cap][2] double with d_n1 / d_n2 [B] valid
+ * points; d_out [B][4] = {N1, N2, count1, count2}, count1 = points of set 1 whose nearest point of set 2 lies within
+ * `thresh` (Euclidean, fp64), count2 the converse.  repeatability = (count1 + count2) / (N1 + N2). */
+SPN_API int spn_repeatability_counts(spn_ctx* ctx, const double* d_pts1, const int32_t* d_n1, const double* d_pts2,
+                                     const int32_t* d_n2, int B, int cap, double thresh, int32_t* d_out, spn_stream stream);
+
+/* cv2.BFMatcher(cv2.NORM_L2, crossCheck=True).match(desc1, desc2) (descriptor_evaluation.py:71-78), batched:
+ * d_desc1 [B][cap1][C], d_desc2 [B][cap2][C] fp32 with d_n1 / d_n2 [B] valid rows, C a multiple of 64.  The distance
+ * matrix is a tcgen05 GEMM on (hi, lo) fp16 splits of the descriptors (fp32-quality dot products), arg-min by 64-bit
+ * atomicMin, ties to the lower index.  d_match [B][cap1] = train index of query i or -1, d_dist [B][cap1] = L2 distance. */
+SPN_API int spn_mutual_nn_match(spn_ctx* ctx, const float* d_desc1, const int32_t* d_n1, const float* d_desc2,
+                                const int32_t* d_n2, int B, int cap1, int cap2, int C, int32_t* d_match, float* d_dist,
+                                spn_stream stream);
+
 /* Per-kernel CUDA-event timing for bench.py's roofline leg.  Slots 0..11 = the convolution of layer SPN_L_*,
  * then the bandwidth-bound kernels.  spn_profile_read synchronises, writes the accumulated milliseconds and launch
  * counts per slot into HOST arrays of SPN_PROF_SLOTS entries and resets the counters. */

@@ -58,6 +58,9 @@ PROTOTYPES = {
     "spn_resize_crop": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp]),
     "spn_invert3x3": (_i, [_vp, _vp, _i, _vp, _vp]),
     "spn_kornia_matrices": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "spn_select_keypoints": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "spn_repeatability_counts": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_double, _vp, _vp]),
+    "spn_mutual_nn_match": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "spn_launch_count": (C.c_int64, [_vp]),
     "spn_profile_enable": (_i, [_vp, _i]),
     "spn_profile_read": (_i, [_vp, _vp, _vp]),
@@ -355,6 +358,55 @@ class Context:
         fwd, bwd = torch.empty_like(h), torch.empty_like(h)
         self._call("spn_kornia_matrices", self.handle, _ptr(h), h.numel() // 9, int(H), int(W), _ptr(fwd), _ptr(bwd), self._s())
         return fwd, bwd
+
+    # ---- on-GPU evaluation (evaluations/*.py of the reference) -----------------------------------
+    SELECT_CAP = 16384
+
+    def select_keypoints(self, prob, warp=None, bounds=None, emit_warped=False, keep_k=300):
+        """prob (B,H,W) fp32 CUDA NMS'd heatmaps; warp: (B,3,3) float64 numpy / tensor on the HOST or None.
+        -> (pts (B,keep_k,2) float64 (row, col), score (B,keep_k), count (B,) int32): select_k_best order (ascending)."""
+        import numpy as np
+        prob = _dense(prob)
+        _chk_dev(prob, torch.float32, "prob", self.device)
+        B, H, W = prob.shape
+        bh, bw = (H, W) if bounds is None else (int(bounds[0]), int(bounds[1]))
+        wptr = None
+        if warp is not None:
+            w = np.ascontiguousarray(np.asarray(warp, dtype=np.float64).reshape(B, 9))
+            wptr = C.c_void_p(w.ctypes.data)
+        dev = prob.device
+        pts = torch.zeros((B, keep_k, 2), dtype=torch.float64, device=dev)
+        score = torch.zeros((B, keep_k), dtype=torch.float32, device=dev)
+        count = torch.zeros((2 * B,), dtype=torch.int32, device=dev)
+        self._call("spn_select_keypoints", self.handle, _ptr(prob), B, H, W, wptr, bh, bw, int(bool(emit_warped)), int(keep_k),
+                   _ptr(pts), _ptr(score), _ptr(count), self._s())
+        return pts, score, count
+
+    def repeatability_counts(self, pts1, n1, pts2, n2, thresh):
+        """-> (B,4) int32 {N1, N2, count1, count2}."""
+        pts1, pts2 = _dense(pts1), _dense(pts2)
+        _chk_dev(pts1, torch.float64, "pts1", self.device)
+        _chk_dev(pts2, torch.float64, "pts2", self.device)
+        B, cap, _ = pts1.shape
+        if pts2.shape[1] != cap:
+            raise NativeError("repeatability_counts: both point sets must have the same capacity")
+        out = torch.zeros((B, 4), dtype=torch.int32, device=pts1.device)
+        self._call("spn_repeatability_counts", self.handle, _ptr(pts1), _ptr(_dense(n1)), _ptr(pts2), _ptr(_dense(n2)), B, cap,
+                   C.c_double(float(thresh)), _ptr(out), self._s())
+        return out
+
+    def mutual_nn_match(self, desc1, n1, desc2, n2):
+        """desc1 (B,cap1,C), desc2 (B,cap2,C) fp32 CUDA -> (match (B,cap1) int32 train index or -1, dist (B,cap1))."""
+        desc1, desc2 = _dense(desc1), _dense(desc2)
+        _chk_dev(desc1, torch.float32, "desc1", self.device)
+        _chk_dev(desc2, torch.float32, "desc2", self.device)
+        B, c1, Cc = desc1.shape
+        c2 = desc2.shape[1]
+        match = torch.empty((B, c1), dtype=torch.int32, device=desc1.device)
+        dist = torch.empty((B, c1), dtype=torch.float32, device=desc1.device)
+        self._call("spn_mutual_nn_match", self.handle, _ptr(desc1), _ptr(_dense(n1)), _ptr(desc2), _ptr(_dense(n2)), B, c1, c2, Cc,
+                   _ptr(match), _ptr(dist), self._s())
+        return match, dist
 
     def resize_crop(self, src: torch.Tensor, new_h, new_w, crop_top, crop_left, H, W, divisor=255.0):
         """src (H0,W0) uint8 or fp32 CUDA -> (H,W) fp32: bilinear resize + centre crop + /divisor (loader pre-processing)."""

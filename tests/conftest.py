@@ -61,3 +61,41 @@ def keypoint_agreement(a, b, tol=1.0):
         return 0.0, 0.0
     d = np.abs(a[:, None, :] - b[None, :, :]).max(-1)
     return float((d.min(1) <= tol).mean()), float((d.min(0) <= tol).mean())
+
+
+def make_eval_pair(seed, h=96, w=128, n_pts=220):
+    """Synthetic HPatches-style evaluation pair (shared by tests/golden/make_golden.py and the GPU tests): an NMS-like
+    sparse ``prob`` map, a ground-truth homography, a ``warped_prob`` whose detections are the mapped points (some
+    jittered, some dropped, some spurious) and dense (H,W,256) descriptor maps whose vectors correspond across the pair
+    up to noise.  numpy RandomState only, so it regenerates bit-identically anywhere."""
+    rng = np.random.RandomState(seed)
+    ang, sc = rng.uniform(-0.25, 0.25), rng.uniform(0.9, 1.1)
+    H = np.array([[sc * np.cos(ang), -sc * np.sin(ang), rng.uniform(-6, 6)],
+                  [sc * np.sin(ang), sc * np.cos(ang), rng.uniform(-5, 5)],
+                  [rng.uniform(-2e-4, 2e-4), rng.uniform(-2e-4, 2e-4), 1.0]]).astype(np.float32)
+    prob = np.zeros((h, w), np.float32)
+    warped_prob = np.zeros((h, w), np.float32)
+    desc = rng.randn(h, w, 256).astype(np.float32)
+    warped_desc = rng.randn(h, w, 256).astype(np.float32)
+    ys, xs = rng.randint(0, h, n_pts), rng.randint(0, w, n_pts)
+    for y, x in zip(ys, xs):
+        if prob[y, x] > 0:
+            continue
+        prob[y, x] = rng.uniform(0.05, 1.0)
+        q = H.astype(np.float64) @ np.array([x, y, 1.0])
+        wx, wy = q[0] / q[2], q[1] / q[2]
+        r = rng.rand()
+        if r < 0.25:
+            continue                                    # not re-detected
+        jy, jx = (rng.randint(-2, 3), rng.randint(-2, 3)) if r < 0.5 else (0, 0)
+        iy, ix = int(round(wy)) + jy, int(round(wx)) + jx
+        if 0 <= iy < h and 0 <= ix < w and warped_prob[iy, ix] == 0:
+            warped_prob[iy, ix] = rng.uniform(0.05, 1.0)
+            warped_desc[iy, ix] = desc[y, x] + 0.35 * rng.randn(256).astype(np.float32)
+    for _ in range(n_pts // 5):                          # spurious detections in the warped image
+        iy, ix = rng.randint(0, h), rng.randint(0, w)
+        if warped_prob[iy, ix] == 0:
+            warped_prob[iy, ix] = rng.uniform(0.05, 1.0)
+    desc /= np.linalg.norm(desc, axis=-1, keepdims=True)
+    warped_desc /= np.linalg.norm(warped_desc, axis=-1, keepdims=True)
+    return {"prob": prob, "warped_prob": warped_prob, "homography": H, "desc": desc, "warped_desc": warped_desc}

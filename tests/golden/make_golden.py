@@ -299,6 +299,46 @@ def main():
     pre["h_out"] = hp.adapt_homography_to_resize(hom).numpy()
     np.savez_compressed(OUT / "preprocess.npz", **pre)
 
+    # ---- 8. export evaluations: detector_evaluation.compute_repeatability and
+    #         descriptor_evaluation.compute_homography of the unmodified reference on synthetic pairs ---------------
+    sys.path.insert(0, str(ROOT / "tests"))
+    from conftest import make_eval_pair
+    from superpoint.evaluations import descriptor_evaluation as ref_desc
+    from superpoint.evaluations import detector_evaluation as ref_det
+    import os
+    ev = {}
+    seeds = [102, 103, 105, 107]        # chosen so that every nearest neighbour is separated by > 5e-5 (see the assert below)
+    ev["seeds"] = np.array(seeds)
+    rep_dir = Path(exper, "repeatability", "golden_eval")
+    os.makedirs(rep_dir, exist_ok=True)
+    ref_det.EXPER_PATH = exper
+    for k, seed in enumerate(seeds):
+        d = make_eval_pair(seed)
+        np.savez(rep_dir / f"pair{k}.npz", prob=d["prob"], warped_prob=d["warped_prob"], homography=d["homography"])
+        for kk, thr in ((300, 3), (50, 1)):                      # per-pair values through a one-file experiment
+            one = Path(exper, "repeatability", f"golden_eval_one{k}")
+            os.makedirs(one, exist_ok=True)
+            np.savez(one / "p.npz", prob=d["prob"], warped_prob=d["warped_prob"], homography=d["homography"])
+            ev[f"rep{k}_k{kk}_t{thr}"] = np.array(ref_det.compute_repeatability(f"golden_eval_one{k}", keep_k_points=kk, distance_thresh=thr))
+        for kk in (1000, 60):
+            r = ref_desc.compute_homography(d, keep_k_points=kk)
+            ev[f"hom{k}_k{kk}_kp1"] = r["keypoints1"]
+            ev[f"hom{k}_k{kk}_kp2"] = r["keypoints2"]
+            ev[f"hom{k}_k{kk}_matches"] = np.array([[m.queryIdx, m.trainIdx] for m in r["matches"]], np.int64).reshape(-1, 2)
+            ev[f"hom{k}_k{kk}_dist"] = np.array([m.distance for m in r["matches"]], np.float32)
+            ev[f"hom{k}_k{kk}_score"] = np.array(r.get("matching_score", 0.0))
+            ev[f"hom{k}_k{kk}_correct"] = np.array(r["correctness"])
+            # robustness of the golden: the nearest neighbours must be separated far beyond fp32 rounding
+            a = d["desc"][r["keypoints1"][:, 0], r["keypoints1"][:, 1]].astype(np.float64)
+            b = d["warped_desc"][r["keypoints2"][:, 0], r["keypoints2"][:, 1]].astype(np.float64)
+            dm = np.sqrt(np.maximum(((a[:, None, :] - b[None, :, :]) ** 2).sum(-1), 0))
+            for mat in (dm, dm.T):
+                srt = np.sort(mat, axis=1)
+                assert (srt[:, 1] - srt[:, 0]).min() > 5e-5, "near-tie in the golden matching case: pick another seed"
+    ev["rep_all_k300_t3"] = np.array(ref_det.compute_repeatability("golden_eval", keep_k_points=300, distance_thresh=3))
+    np.savez_compressed(OUT / "eval_cases.npz", **ev)
+    print({k: (v.tolist() if v.size == 1 else v.shape) for k, v in ev.items() if k.startswith("rep") or k.endswith("score")})
+
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 
