@@ -6,9 +6,9 @@
 Same YAML schema as the reference (``data``, ``homography_adaptation``, ``model``, ``pretrained``).  What differs:
   * ``model.script`` / ``model.class_name`` resolve inside this package (models/SuperPoint.py), so an unmodified
     reference config selects the B200 implementation;
-  * the data loaders (COCO / HPatches image decoding) are out of scope: if the reference
-    package is importable its ``get_loader`` is used, otherwise ``--synthetic N`` feeds N synthetic images of the
-    configured size;
+  * ``get_loader`` is this package's (utils/data_loaders.py): the reference's COCO / HPatches dataset classes mirrored for
+    the export tasks, decoding on host threads and resizing on the GPU; ``--synthetic N`` feeds N synthetic images of
+    the configured size instead;
   * ``train`` and ``export_NeRF_labels`` are out of scope: their flags (``--training.*``) parse exactly as in the
     reference, the task itself is rejected at dispatch;
   * under ``torchrun`` (WORLD_SIZE > 1) every rank selects ``cuda:LOCAL_RANK``, joins the NCCL process group and takes
@@ -155,15 +155,8 @@ def main(config_path: str,
     if synthetic:
         loader = SyntheticLoader(synthetic, config["data"]["preprocessing"]["resize"], task, rank, world)
     else:
-        try:
-            from superpoint.utils.data_loaders import get_loader  # the reference's loaders, if installed
-        except ImportError as e:
-            raise SystemExit("dataset loaders are out of scope here: install the reference package for COCO/HPatches "
-                             f"loading or pass --synthetic N ({e})")
-        loader = get_loader(config, task, device="cpu", export_split=pseudo_labels.split) if task == "export_pseudo_labels" \
-            else get_loader(config, task, device="cpu")
-        if world > 1:
-            loader = ShardedLoader(loader, rank, world)
+        from .utils.data_loaders import get_loader
+        loader = get_loader(config, task, device=device, export_split=pseudo_labels.split, rank=rank, world=world)
     if task == "export_pseudo_labels":
         if world > 1:   # device-sampler key = global dataset index: rank-strided items, see ExportDetections
             config.setdefault("homography_adaptation", {}).update(index_stride=world, index_offset=rank)

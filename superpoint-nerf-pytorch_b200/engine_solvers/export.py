@@ -4,6 +4,17 @@ ExportDetections              homography-adaptation pseudo-labels -> <EXPER_PATH
 Export_Hpatches_Repeatability two forwards per pair               -> <EXPER_PATH>/repeatability/<experiment>/<name>.npz
 Export_Hpatches_Descriptors   + dense descriptors (H,W,256)       -> <EXPER_PATH>/descriptors/<experiment>/<name>.npz
 
+Optional on-disk formats (extension keys under ``data``; the defaults are the reference's layouts):
+  ``packed: true``   ExportDetections additionally writes ONE file per rank, ``<split>/packed_rank<r>.npz`` with
+                     ``names`` (n,), ``keypoints`` (N,2) int32 (row, col), ``offsets`` (n+1,) into ``keypoints`` and
+                     ``global_offset`` = this rank's base in the concatenation over ranks (the all_gather of per-rank
+                     counts, utils/sharding.gather_export_counts); ``per_image_files: false`` then skips the .npy files.
+                     ``load_packed_labels`` reads the shards back as {name: (N,2) int64}.
+  ``sparse: true``   Export_Hpatches_Descriptors stores ``keypoints`` (k,2) int32 / ``desc_sparse`` (k,256) (and the
+                     ``warped_`` twins) - the descriptors AT the post-NMS keypoints, which is all that
+                     descriptor_evaluation.compute_homography reads - instead of two dense (H,W,256) maps
+                     (2 x 315 MB per 480x640 pair -> ~2 MB).  evaluations/descriptor_evaluation.py consumes both layouts.
+
 What changes underneath: the 99 sequential batch-1 steps of the reference (export.py:103-104) become ONE batched
 pass per group of images - warp_batch -> encoder/head over all (image, homography) pairs -> fused inverse-warp
 aggregation -> NMS/threshold/compaction - every stage a kernel behind include/spn_b200.h.  The in-model box_nms
@@ -192,7 +203,12 @@ class ExportDetections:
         self.engine = HomographyAdaptation(config, model, device)
         self.one_homography = self.engine.sampler
         self._stage_slots, self._stage_next = [{}, {}, {}], 0
+        self.packed = bool(config["data"].get("packed", False))
+        self.per_image_files = bool(config["data"].get("per_image_files", True)) or not self.packed
+        self._packed_names, self._packed_kp = [], []
         self.homography_adaptation()
+        if self.packed:
+            self._write_packed()
 
     def _init_output_dir(self):
         out = Path(settings.EXPER_PATH, "outputs", self.config["data"]["experiment_name"], self.split)
@@ -231,7 +247,24 @@ class ExportDetections:
     def _finish(self, pending):
         paths, handle = pending
         for path, kp in zip(paths, self.engine.keypoints_wait(handle)):
-            np.save(path, kp)
+            if self.per_image_files:
+                np.save(path, kp)
+            if self.packed:
+                self._packed_names.append(Path(path).stem)
+                self._packed_kp.append(kp.astype(np.int32))
+
+    def _write_packed(self):
+        """One packed shard per rank; global offsets from the all_gather of per-rank (images, keypoints) counts."""
+        from ..utils.sharding import gather_export_counts
+        import torch.distributed as dist
+        counts = np.array([len(k) for k in self._packed_kp], np.int64)
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        dev = self.device if rank or (dist.is_available() and dist.is_initialized()) else "cpu"
+        allc, offs = gather_export_counts(len(counts), int(counts.sum()), device=dev)
+        kp = np.concatenate(self._packed_kp) if self._packed_kp else np.zeros((0, 2), np.int32)
+        np.savez(Path(self.output_dir, f"packed_rank{rank:03d}.npz"), names=np.array(self._packed_names), keypoints=kp,
+                 offsets=np.concatenate([[0], np.cumsum(counts)]), global_offset=np.array(int(offs[rank])),
+                 counts_all_ranks=allc.cpu().numpy())
 
     @torch.no_grad()
     def homography_adaptation(self):
@@ -256,7 +289,7 @@ class ExportDetections:
         for seen, data in enumerate(tqdm(self.dataloader, desc="Exporting detections", colour="green")):
             name = data["name"][0]
             save_path = Path(self.output_dir, f"{name}.npy")
-            if save_path.exists():                     # resume by file existence (export.py:89-91)
+            if self.per_image_files and save_path.exists():   # resume by file existence (export.py:89-91)
                 flush()                                # keeps the indices of a group consecutive
                 continue
             image = data["raw"]["image"]              # moved to the device per group (see _stage), not per image
@@ -342,11 +375,28 @@ class Export_Hpatches_Descriptors:
 
     @torch.no_grad()
     def export_descriptors(self):
+        sparse = bool(self.config["data"].get("sparse", False))
         writer = _NpzWriter(workers=max(1, min(4, (os.cpu_count() or 2) - 1)), depth=4)   # ~630 MB per pair in flight
         try:
             for i, data in enumerate(tqdm(self.dataloader, desc="Exporting HPatches descriptors", colour="green")):
                 data = move_to_device(data, self.device)
                 both = torch.cat([data["image"], data["warped_image"]], dim=0)
+                if sparse:                            # one C-ABI call: forward + NMS/top-k once + descriptors at keypoints
+                    out = self.model(both, keypoints=True)
+                    det, des = out["detector_output"], out["descriptor_output"]
+                    n = det["keypoint_count"].cpu().numpy()
+                    cap = det["keypoints"].shape[1]
+                    if n.max() > cap:
+                        raise RuntimeError(f"{int(n.max())} keypoints exceed the list capacity {cap}: set detector_head.top_k")
+                    kp, ds = det["keypoints"].cpu().numpy(), des["desc_sparse"].cpu().numpy()
+                    output = {"image": _np(data["image"]), "warped_image": _np(data["warped_image"]),
+                              "prob": _np(det["prob_heatmap_nms"][0]), "warped_prob": _np(det["prob_heatmap_nms"][1]),
+                              "keypoints": kp[0, :n[0]], "desc_sparse": ds[0, :n[0]],
+                              "warped_keypoints": kp[1, :n[1]], "warped_desc_sparse": ds[1, :n[1]],
+                              "homography": _np(data["homography"])}
+                    filename = data["name"][0] if "name" in data else str(i)
+                    writer.save(Path(self.output_dir, f"{filename}.npz"), output)
+                    continue
                 out = self.model(both)
                 probs = out["detector_output"]["prob_heatmap_nms"]
                 desc = out["descriptor_output"]["desc"]
@@ -358,3 +408,15 @@ class Export_Hpatches_Descriptors:
                 writer.save(Path(self.output_dir, f"{filename}.npz"), output)
         finally:
             writer.close()
+
+
+def load_packed_labels(directory):
+    """Read every ``packed_rank*.npz`` shard of an ExportDetections run -> {name: (N,2) int64 (row, col)} - the same
+    arrays the per-image ``<name>.npy`` files hold (what data/COCO.py:100-102 of the reference loads as labels)."""
+    out = {}
+    for f in sorted(Path(directory).glob("packed_rank*.npz")):
+        z = np.load(f)
+        off = z["offsets"]
+        for i, name in enumerate(z["names"]):
+            out[str(name)] = z["keypoints"][off[i]:off[i + 1]].astype(np.int64)
+    return out

@@ -220,3 +220,53 @@ def test_sharded_loader_partitions_items():
     items = list(range(11))
     parts = [list(ShardedLoader(items, r, 3)) for r in range(3)]
     assert sorted(sum(parts, [])) == items and [len(ShardedLoader(items, r, 3)) for r in range(3)] == [len(p) for p in parts]
+
+
+def test_prefetch_loader_order_sharding_and_dataset_listing(tmp_path, monkeypatch):
+    from superpoint_nerf_pytorch_b200 import settings
+    from superpoint_nerf_pytorch_b200.utils.data_loaders import PrefetchLoader
+
+    class Fake:
+        def __len__(self):
+            return 23
+
+        def decode(self, i):
+            return i
+
+        def finish(self, d):
+            return {"v": d * 10}
+
+        def batch_collator(self, batch):
+            return [b["v"] for b in batch]
+
+    assert list(PrefetchLoader(Fake(), batch_size=1, workers=4)) == [[10 * i] for i in range(23)]
+    assert sum(list(PrefetchLoader(Fake(), batch_size=4, workers=3)), []) == [10 * i for i in range(23)]
+    parts = [sum(list(PrefetchLoader(Fake(), 1, workers=2, rank=r, world=3)), []) for r in range(3)]
+    assert sorted(sum(parts, [])) == [10 * i for i in range(23)] and parts[1][0] == 10
+    assert len(PrefetchLoader(Fake(), 4, rank=1, world=3)) == 2
+    # dataset listing (COCO.py:34-56): <DATA_PATH>/<name>/images/<split>/*
+    import cv2
+    d = tmp_path / "COCO" / "images" / "validation"
+    d.mkdir(parents=True)
+    for k in range(4):
+        cv2.imwrite(str(d / f"im{k}.jpg"), np.full((20, 30), 40 * k, np.uint8))
+    monkeypatch.setattr(settings, "DATA_PATH", str(tmp_path))
+    from superpoint_nerf_pytorch_b200.data.COCO import COCO
+    cfg = {"name": "COCO", "preprocessing": {"resize": [16, 24]}, "has_labels": False, "warped_pair": False, "truncate": 0.5,
+           "augmentation": {"photometric": {"enable": False}, "homographic": {"enable": False}}}
+    ds = COCO(cfg, task="validation", device="cpu")
+    assert len(ds) == 2 and all(n.startswith("im") for n in ds.samples["names"])
+    img, name = ds.decode(0)
+    assert img.dtype == torch.uint8 and tuple(img.shape) == (20, 30) and name in ("im0", "im1", "im2", "im3")
+    with pytest.raises(NotImplementedError):
+        COCO(dict(cfg, has_labels="outputs/x"), task="training")
+
+
+def test_packed_label_reader(tmp_path):
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import load_packed_labels
+    a, b, c = np.array([[1, 2], [3, 4]], np.int32), np.zeros((0, 2), np.int32), np.array([[7, 8]], np.int32)
+    np.savez(tmp_path / "packed_rank000.npz", names=np.array(["x", "y"]), keypoints=np.concatenate([a, b]), offsets=np.array([0, 2, 2]),
+             global_offset=np.array(0))
+    np.savez(tmp_path / "packed_rank001.npz", names=np.array(["z"]), keypoints=c, offsets=np.array([0, 1]), global_offset=np.array(2))
+    got = load_packed_labels(tmp_path)
+    assert sorted(got) == ["x", "y", "z"] and np.array_equal(got["x"], a) and got["y"].shape == (0, 2) and got["z"].dtype == np.int64

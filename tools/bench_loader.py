@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Does the loader keep the export fed?  
+
+Writes N synthetic 640x480 JPEGs, then measures (a) the prefetching COCO loader alone (decode on host threads + resize
+kernel) and (b) the ExportDetections task (f16, 100 homographies, 240x320) driven by that loader, .npy writes included.
+
+    python tools/bench_loader.py [--n 1024] [--workers W]
+"""
+import argparse
+import copy
+import json
+import shutil
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+from superpoint_nerf_pytorch_b200 import settings  # noqa: E402
+from superpoint_nerf_pytorch_b200.engine_solvers.export import ExportDetections  # noqa: E402
+from superpoint_nerf_pytorch_b200.utils.data_loaders import get_loader  # noqa: E402
+from superpoint_nerf_pytorch_b200.utils.get_model import get_model  # noqa: E402
+
+
+def main():
+    import cv2
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1024)
+    ap.add_argument("--workers", type=int, default=0)
+    args = ap.parse_args()
+    tmp = Path(tempfile.mkdtemp(prefix="spn_loader_"))
+    try:
+        d = tmp / "data" / "COCO" / "images" / "training"
+        d.mkdir(parents=True)
+        rng = np.random.RandomState(0)
+        base = cv2.GaussianBlur(rng.randint(0, 256, (480, 640, 3)).astype(np.uint8), (0, 0), 2.0)
+        for k in range(args.n):
+            cv2.imwrite(str(d / f"im{k:06d}.jpg"), np.roll(base, k * 7, axis=1), [cv2.IMWRITE_JPEG_QUALITY, 90])
+        settings.DATA_PATH, settings.EXPER_PATH = str(tmp / "data"), str(tmp / "exper")
+        data = {"name": "COCO", "class_name": "COCO", "experiment_name": "loader_bench", "preprocessing": {"resize": [240, 320]},
+                "has_labels": False, "warped_pair": False, "batch_size": 1, "truncate": False,
+                "augmentation": {"photometric": {"enable": False}, "homographic": {"enable": False}}}
+        if args.workers:
+            data["loader_workers"] = args.workers
+        mcfg = dict(copy.deepcopy(bench.MODEL_CFG), precision="f16")
+        cfg = {"data": data, "model": mcfg,
+               "homography_adaptation": dict(copy.deepcopy(bench.HA_CFG), sampler="device", seed=1, images_per_launch=32, max_forwards=100)}
+        loader = get_loader(cfg, "export_pseudo_labels", device="cuda", export_split="training")
+        for _ in zip(range(32), loader):
+            pass
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = sum(b["raw"]["image"].shape[0] for b in loader)
+        torch.cuda.synchronize()
+        t_load = time.perf_counter() - t0
+        model = get_model(mcfg, "cuda").eval()
+        model.load_state_dict(bench.random_init_state_dict())
+        warm = copy.deepcopy(cfg)
+        warm["data"]["experiment_name"] = "warm"
+        ExportDetections(warm, model, list(zip(range(64), loader)) and [b for _, b in zip(range(64), loader)], "training", True, "cuda")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ExportDetections(cfg, model, loader, "training", True, "cuda")
+        torch.cuda.synchronize()
+        t_exp = time.perf_counter() - t0
+        files = len(list(Path(tmp, "exper", "outputs", "loader_bench", "training").glob("*.npy")))
+        print(json.dumps({"images": n, "loader_only_img_per_s": n / t_load, "export_with_loader_img_per_s": files / t_exp,
+                          "files_written": files, "workers": loader.workers, "jpeg": "640x480 q90 -> 240x320",
+                          "note": "export = decode (host threads) + resize kernel + HA x100 (f16) + NMS + .npy per image"}))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()
