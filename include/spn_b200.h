@@ -150,7 +150,8 @@ SPN_API int spn_nms_stats(spn_ctx* ctx, int B, int H, int W, int64_t* h_out);
  * warped pixels are BIT-IDENTICAL to the reference's CPU run when Ainv carries the reference's bits.
  * d_images [n_images][H][W]; d_warped [n_images*(n_h+1)][H][W] fp32; d_mask same shape u8.  d_warped may be NULL
  * (mask only: the fused encoder spn_encoder_forward_ha warps on the fly).
- * Limits: 1 <= margin <= 8, n_images*(n_h+1) <= 65535 per call, W <= 8192, H, W >= 2. */
+ * margin = 0 skips the erosion (Homographic_aug.compute_valid_mask with erosion = 0, homographic_augmentation.py:109-127).
+ * Limits: 0 <= margin <= 8, n_images*(n_h+1) <= 65535 per call, W <= 8192, H, W >= 2. */
 SPN_API int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images, const float* d_ainv, int n_h, int H, int W,
                    int margin, float* d_warped, uint8_t* d_mask, spn_stream stream);
 
@@ -223,6 +224,13 @@ SPN_API int spn_repeatability_counts(spn_ctx* ctx, const double* d_pts1, const i
 SPN_API int spn_mutual_nn_match(spn_ctx* ctx, const float* d_desc1, const int32_t* d_n1, const float* d_desc2,
                                 const int32_t* d_n2, int B, int cap1, int cap2, int C, int32_t* d_match, float* d_dist,
                                 spn_stream stream);
+
+/* Detector-loss label building (utils/losses.py:13-27): d_kpts_heatmap [B][H][W] int32 (0/1), d_valid_mask [B][H][W] int32
+ * (nullable = all valid), d_noise [B][65][H/8][W/8] fp32 (nullable: the U(0, 0.1) tie-break noise is drawn from a
+ * counter-based generator keyed by `seed`).  d_labels [B][H/8][W/8] int64 = argmax over the 65 classes of
+ * cat([2 * pixel_unshuffle(heatmap), 1]) + noise; d_valid_cells [B][H/8][W/8] fp32 = product of the mask over the cell. */
+SPN_API int spn_detector_labels(spn_ctx* ctx, const int32_t* d_kpts_heatmap, const int32_t* d_valid_mask, const float* d_noise,
+                                uint64_t seed, int B, int H, int W, int64_t* d_labels, float* d_valid_cells, spn_stream stream);
 
 /* Per-kernel CUDA-event timing for bench.py's roofline leg.  Slots 0..11 = the convolution of layer SPN_L_*,
  * then the bandwidth-bound kernels.  spn_profile_read synchronises, writes the accumulated milliseconds and launch

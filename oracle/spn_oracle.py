@@ -463,3 +463,29 @@ def adapt_homography_to_resize(homography, image_shape, warped_image_shape, targ
     wt[0, -1] = -((source_warped_size[1] * ws - target_size[1]) / torch.tensor(2.0)).to(torch.int32)
     wt[1, -1] = -((source_warped_size[0] * ws - target_size[0]) / torch.tensor(2.0)).to(torch.int32)
     return wt @ down @ torch.as_tensor(homography, dtype=torch.float32) @ up @ t
+
+
+# --------------------------------------------------------------------------------------------
+# Train-time reuse: detector-loss label building, utils/losses.py:6-38
+# --------------------------------------------------------------------------------------------
+
+def detector_labels(kpts_heatmap, valid_mask=None, grid_size=8, include_mask=False, noise=None):
+    """losses.py:13-27: per-cell class labels (argmax with a random U(0, 0.1) tie break) and the valid-cell mask.
+    ``noise`` None draws it exactly like the reference (torch.distributions under torch's global RNG)."""
+    labels = kpts_heatmap.unsqueeze(1).to(torch.float32)
+    labels = torch.pixel_unshuffle(labels, grid_size)
+    B, _, Hc, Wc = labels.shape
+    labels = torch.cat([2 * labels, torch.ones(size=[B, 1, Hc, Wc])], dim=1)
+    if noise is None:
+        noise = torch.distributions.uniform.Uniform(0, 0.1).sample(labels.shape)
+    labels = torch.argmax(labels + noise, dim=1)
+    vm = torch.ones_like(kpts_heatmap) if (include_mask is False or valid_mask is None) else valid_mask
+    vm = torch.prod(torch.pixel_unshuffle(vm.unsqueeze(1).to(torch.float32), grid_size), dim=1)
+    return labels, vm, noise
+
+
+def detector_loss(logits, kpts_heatmap, valid_mask, grid_size=8, include_mask=False, noise=None):
+    """losses.py:6-38 (the loss itself, used only to pin ``detector_labels`` against the reference)."""
+    labels, vm, _ = detector_labels(kpts_heatmap, valid_mask, grid_size, include_mask, noise)
+    det = F.cross_entropy(logits, labels, reduction="none")
+    return torch.mean(torch.divide(torch.sum(det * vm, dim=(1, 2)), torch.sum(vm, dim=(1, 2)) + 1e-10))

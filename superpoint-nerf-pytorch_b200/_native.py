@@ -61,6 +61,7 @@ PROTOTYPES = {
     "spn_select_keypoints": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "spn_repeatability_counts": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_double, _vp, _vp]),
     "spn_mutual_nn_match": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "spn_detector_labels": (_i, [_vp, _vp, _vp, _vp, C.c_uint64, _i, _i, _i, _vp, _vp, _vp]),
     "spn_launch_count": (C.c_int64, [_vp]),
     "spn_profile_enable": (_i, [_vp, _i]),
     "spn_profile_read": (_i, [_vp, _vp, _vp]),
@@ -358,6 +359,24 @@ class Context:
         fwd, bwd = torch.empty_like(h), torch.empty_like(h)
         self._call("spn_kornia_matrices", self.handle, _ptr(h), h.numel() // 9, int(H), int(W), _ptr(fwd), _ptr(bwd), self._s())
         return fwd, bwd
+
+    def detector_labels(self, kpts_heatmap, valid_mask=None, noise=None, seed=0):
+        """utils/losses.py:13-27 label building: kpts_heatmap (B,H,W) int32, valid_mask (B,H,W) int32 or None, noise
+        (B,65,H/8,W/8) fp32 or None -> (labels (B,H/8,W/8) int64, valid cells (B,H/8,W/8) fp32)."""
+        kpts_heatmap = _dense(kpts_heatmap)
+        _chk_dev(kpts_heatmap, torch.int32, "kpts_heatmap", self.device)
+        B, H, W = kpts_heatmap.shape
+        if valid_mask is not None:
+            valid_mask = _dense(valid_mask)
+            _chk_dev(valid_mask, torch.int32, "valid_mask", self.device)
+        if noise is not None:
+            noise = _dense(noise)
+            _chk_dev(noise, torch.float32, "noise", self.device)
+        labels = torch.empty((B, H // 8, W // 8), dtype=torch.int64, device=kpts_heatmap.device)
+        cells = torch.empty((B, H // 8, W // 8), dtype=torch.float32, device=kpts_heatmap.device)
+        self._call("spn_detector_labels", self.handle, _ptr(kpts_heatmap), _ptr(valid_mask), _ptr(noise), C.c_uint64(seed), B, H, W,
+                   _ptr(labels), _ptr(cells), self._s())
+        return labels, cells
 
     # ---- on-GPU evaluation (evaluations/*.py of the reference) -----------------------------------
     SELECT_CAP = 16384

@@ -36,6 +36,13 @@ struct ErodeK {
 ErodeK make_ellipse(int margin) {
   ErodeK e;
   memset(&e, 0, sizeof(e));
+  if (margin == 0) {  // no erosion (compute_valid_mask with erosion = 0): the 1x1 structuring element
+    e.ks = 1;
+    e.org = 0;
+    e.rw_magic = (uint32_t)(((1ull << 32) + kTileW - 1) / kTileW);
+    e.rows[0] = 1u;
+    return e;
+  }
   const int ks = 2 * margin;
   e.ks = ks;
   e.org = ks / 2;
@@ -617,7 +624,7 @@ extern "C" int spn_warp_batch(spn_ctx* ctx, const float* d_images, int n_images,
     if (rc) return rc;
   }
   // the reference's valid_border_margin == 0 path is shape-broken: unsupported
-  SPN_REQUIRE(margin >= 1 && 2 * margin <= kMaxKs, "spn_warp_batch: valid_border_margin must be in [1,%d]", kMaxKs / 2);
+  SPN_REQUIRE(margin >= 0 && 2 * margin <= kMaxKs, "spn_warp_batch: valid_border_margin must be in [0,%d]", kMaxKs / 2);
   SPN_REQUIRE((size_t)n_images * (n_h + 1) <= 65535, "spn_warp_batch: too many slots per launch");
   const ErodeK ek = make_ellipse(margin);
   const int tiles_x = spn_cdiv(W, kTileW), tiles_y = spn_cdiv(H, kTileH);

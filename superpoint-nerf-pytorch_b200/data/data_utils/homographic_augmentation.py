@@ -2,12 +2,16 @@
 
 ``sample_homography`` keeps the reference's host-side semantics *including its numpy-global-RNG draw order*, so
 ``np.random.seed(s)`` reproduces the reference's matrices bit for bit; ``sample_homographies_device`` is the
-batched device sampler (spn_sample_homographies) used by the throughput path.
+batched device sampler (spn_sample_homographies) used by the throughput path.  ``compute_valid_mask`` and ``__call__``
+(the train-time augmentation of homographic_augmentation.py:109-151) run on the same spn_warp_batch kernel as the export:
+warped image and eroded validity mask in one pass, bit-identical to the reference's CPU result.
 """
 import numpy as np
 import torch
 
 from ..._native import get_context
+from ...utils.kornia_geometry import sampling_matrices
+from .kp_utils import compute_keypoint_map, filter_points, warp_points
 
 _TN_LO, _TN_HI = -2.0, 2.0  # std_trunc = 2 (homographic_augmentation.py:25)
 
@@ -103,3 +107,37 @@ class Homographic_aug:
         p = dict(self.config)
         p.update(params)
         return get_context(self.device).sample_homographies(p, seed, first_index, count, int(shape[0]), int(shape[1]))
+
+    def _warp(self, images, homography, erosion, want_warped):
+        """images (B,H,W) CUDA fp32, homography (B,3,3) -> (warped (B,H,W) or None, mask (B,H,W) u8): one homography per
+        image through spn_warp_batch (slot layout: image b owns slots 2b (identity) and 2b+1 (its warp))."""
+        B, H, W = images.shape
+        fwd, _ = sampling_matrices(homography, (H, W))                      # the reference's torch calls, on the host
+        ctx = get_context(images.device)
+        warped, mask = ctx.warp_batch(images, fwd.to(images.device).view(B, 1, 3, 3), int(erosion), want_warped=want_warped)
+        return (warped.view(B, 2, H, W)[:, 1] if want_warped else None), mask.view(B, 2, H, W)[:, 1]
+
+    def compute_valid_mask(self, shape, homography, erosion=2):
+        """homographic_augmentation.py:109-127 -> (B,1,H,W) int32."""
+        if homography.dim() == 2:
+            homography = homography.unsqueeze(0)
+        dev = torch.device(self.device)
+        if dev.type != "cuda":
+            raise RuntimeError("Homographic_aug runs its warps on CUDA only (no CPU fallback)")
+        ones = torch.empty((homography.shape[0], int(shape[0]), int(shape[1])), dtype=torch.float32, device=dev)
+        _, mask = self._warp(ones, homography, erosion, want_warped=False)
+        return mask.unsqueeze(1).to(torch.int32)
+
+    def __call__(self, image, points):
+        """homographic_augmentation.py:130-151: image (1,1,H,W) on the device, points (N,2) (row, col)."""
+        H, W = (int(v) for v in image.shape[2:])
+        homography = self.sample_homography_host((H, W), **self.config)          # (1,3,3), numpy RNG order of the reference
+        img = image.detach().to(self.device, torch.float32).contiguous().view(1, H, W)
+        warped_image, mask = self._warp(img, homography, self.erosion, want_warped=True)
+        homography = homography.to(img.device)
+        warped_points = warp_points(points.to(img.device), homography, device=img.device)
+        warped_points = filter_points(warped_points, (H, W), device=img.device)
+        heatmap = compute_keypoint_map(warped_points, (H, W), device=img.device)
+        return {"warp": {"image": warped_image.squeeze(), "kpts": warped_points, "kpts_heatmap": heatmap,
+                         "valid_mask": mask.squeeze().to(torch.int32)},
+                "homography": homography.squeeze()}

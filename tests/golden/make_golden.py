@@ -339,6 +339,42 @@ def main():
     np.savez_compressed(OUT / "eval_cases.npz", **ev)
     print({k: (v.tolist() if v.size == 1 else v.shape) for k, v in ev.items() if k.startswith("rep") or k.endswith("score")})
 
+    # ---- 9. train-time reuse: Homographic_aug.__call__ / compute_valid_mask, detector_loss labels --
+    from superpoint.utils.losses import detector_loss as ref_detector_loss
+    tr = {}
+    aug_t = Homographic_aug({"params": dict(HA_CFG["params"], allow_artifacts=False, patch_ratio=0.7), "valid_border_margin": 2}, "cpu")
+    img255 = torch.from_numpy(smooth_image(96, 128, 71) * 255.0)[None, None]
+    prs = np.random.RandomState(8)
+    pts = torch.from_numpy(np.stack([prs.uniform(0, 95, 60), prs.uniform(0, 127, 60)], 1).astype(np.float32))
+    np.random.seed(31)
+    outa = aug_t(img255, pts)
+    tr["aug_image"] = img255.numpy()
+    tr["aug_points"] = pts.numpy()
+    tr["aug_np_seed"] = np.array(31)
+    tr["aug_warped"] = outa["warp"]["image"].numpy()
+    tr["aug_kpts"] = outa["warp"]["kpts"].numpy()
+    tr["aug_heatmap"] = outa["warp"]["kpts_heatmap"].numpy()
+    tr["aug_valid_mask"] = outa["warp"]["valid_mask"].numpy()
+    tr["aug_homography"] = outa["homography"].numpy()
+    np.random.seed(32)
+    Hb = torch.cat([aug_t.sample_homography((96, 128), **HA_CFG["params"]) for _ in range(3)])
+    tr["vm_H"] = Hb.numpy()
+    for er in (0, 2, 3):
+        tr[f"vm_e{er}"] = aug_t.compute_valid_mask((96, 128), Hb, erosion=er).numpy().astype(np.uint8)
+    g9 = torch.Generator().manual_seed(9)
+    kmap = (torch.rand((2, 48, 64), generator=g9) < 0.03).to(torch.int32)
+    vmask = (torch.rand((2, 48, 64), generator=g9) < 0.97).to(torch.int32)
+    logits9 = torch.randn((2, 65, 6, 8), generator=g9)
+    torch.manual_seed(77)
+    tr["loss_ref_masked"] = ref_detector_loss(logits9, kmap, vmask, include_mask=True).numpy()
+    torch.manual_seed(77)
+    labels9, cells9, noise9 = O.detector_labels(kmap, vmask, include_mask=True)
+    torch.manual_seed(77)
+    assert torch.equal(O.detector_loss(logits9, kmap, vmask, include_mask=True), torch.as_tensor(tr["loss_ref_masked"]))
+    tr.update(lab_kmap=kmap.numpy(), lab_valid=vmask.numpy(), lab_logits=logits9.numpy(), lab_noise=noise9.numpy(),
+              lab_labels=labels9.numpy(), lab_cells=cells9.numpy())
+    np.savez_compressed(OUT / "train_reuse.npz", **tr)
+
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

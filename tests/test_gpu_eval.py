@@ -96,7 +96,7 @@ def test_mutual_nn_match_vs_cv2_and_properties():
         assert dm[i, match[i]] <= dm[i].min() + 3e-5 and dm[i, match[i]] <= dm[:, match[i]].min() + 3e-5
     # identity
     m2, d2 = ctx.mutual_nn_match(da, n, da, n)
-    assert np.array_equal(m2[0].cpu().numpy(), np.arange(1000)) and float(d2.max()) < 2e-3
+    assert np.array_equal(m2[0].cpu().numpy(), np.arange(1000)) and float(d2.max()) < 4e-3   # sqrt of a ~4e-6 residual
     # ragged batch: counts smaller than the capacity, an empty set
     n1 = torch.tensor([37, 0], dtype=torch.int32, device="cuda")
     n2 = torch.tensor([129, 50], dtype=torch.int32, device="cuda")

@@ -82,10 +82,11 @@ def test_hpatches_loader_and_sparse_descriptor_layout(tmp_path, monkeypatch):
     for seq, (h, w) in (("v_a", (150, 200)), ("v_b", (135, 180)), ("i_c", (150, 200))):
         (root / seq).mkdir(parents=True)
         base = (smooth_image(h, w, 500 + len(seq)) * 255).astype(np.uint8)
-        cv2.imwrite(str(root / seq / "1.ppm"), base)
+        base = np.stack([base, np.roll(base, 3, 0), np.roll(base, 5, 1)], -1)            # .ppm holds BGR
+        assert cv2.imwrite(str(root / seq / "1.ppm"), base)
         for i in range(2, 7):
             Hm = np.array([[1 + 0.02 * i, 0.01 * i, 2.0 * i], [-0.01 * i, 1 - 0.01 * i, -1.5 * i], [1e-5 * i, -2e-5, 1.0]])
-            cv2.imwrite(str(root / seq / f"{i}.ppm"), cv2.warpPerspective(base, Hm, (w, h)))
+            assert cv2.imwrite(str(root / seq / f"{i}.ppm"), cv2.warpPerspective(base, Hm, (w, h)))
             np.savetxt(str(root / seq / f"H_1_{i}"), Hm)
     monkeypatch.setattr(settings, "DATA_PATH", str(tmp_path / "data"))
     monkeypatch.setattr(settings, "EXPER_PATH", str(tmp_path / "exper"))

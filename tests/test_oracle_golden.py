@@ -134,3 +134,14 @@ def test_preprocessing_matches_reference(golden):
         assert np.array_equal(out.numpy(), g[f"out{k}"]), k
     h = O.adapt_homography_to_resize(g["h_in"], [480.0, 640.0], [427.0, 600.0], (240, 320))
     assert np.array_equal(h.numpy(), g["h_out"])
+
+
+def test_detector_labels_restatement_matches_reference_loss(golden):
+    """oracle.detector_labels / detector_loss (losses.py:6-38 restated) reproduce the reference's loss on the same torch
+    seed, and the committed labels are what the restatement yields for the committed noise."""
+    g = golden("train_reuse.npz")
+    kmap, valid, logits = (torch.from_numpy(g[k]) for k in ("lab_kmap", "lab_valid", "lab_logits"))
+    torch.manual_seed(77)
+    assert torch.equal(O.detector_loss(logits, kmap, valid, include_mask=True), torch.as_tensor(g["loss_ref_masked"]))
+    labels, cells, _ = O.detector_labels(kmap, valid, include_mask=True, noise=torch.from_numpy(g["lab_noise"]))
+    assert np.array_equal(labels.numpy(), g["lab_labels"]) and np.array_equal(cells.numpy(), g["lab_cells"])
