@@ -582,7 +582,9 @@ int spn_tc_encoder_slots(spn_ctx* ctx, const float* d_images, const float* d_hin
     if ((rc = launch_conv_tc(ctx, 1, mode, A, Bq, B, H, W, true, true, 0, s))) return rc;
   } else {
     // warp + block_1 + block_2 in one kernel (front_tc.cu): block_1's output never reaches HBM
-    if ((rc = spn_front_tc_launch(ctx, d_images, d_hinv, n_h, slot_begin, n_slots, H, W, mode, st->w1img[bf], Bq, s))) return rc;
+    rc = ctx->opt_front_pair ? spn_front2_tc_launch(ctx, d_images, d_hinv, n_h, slot_begin, n_slots, H, W, mode, st->w1img[bf], Bq, s)
+                             : spn_front_tc_launch(ctx, d_images, d_hinv, n_h, slot_begin, n_slots, H, W, mode, st->w1img[bf], Bq, s);
+    if (rc) return rc;
   }
   if ((rc = launch_conv_tc(ctx, 2, mode, Bq, A, B, H / 2, W / 2, true, false, 0, s))) return rc;
   if ((rc = launch_conv_tc(ctx, 3, mode, A, Bq, B, H / 2, W / 2, true, true, 0, s))) return rc;

@@ -160,7 +160,16 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ ai
   const int y = ty0 + ty;
   const float* src = images + (size_t)img * H * W;
   const size_t orow = ((size_t)slot * H + y) * W;
+  // mask-only calls (the fused encoder warps on the fly): uniform tiles are written as 16-byte chunks of the 8 image
+  // rows of this block (one contiguous span), only tiles cut by the quad border take the per-pixel path below
+  const bool vec = warped == nullptr && (W & 15) == 0;
+  const int chunks_per_row = W >> 4, block_rows = min(kTileH, H - ty0);
   if (j == 0) {  // identity forward (export.py:93): the image itself, no mask
+    if (vec) {
+      for (int c = threadIdx.x; c < block_rows * chunks_per_row; c += blockDim.x)
+        reinterpret_cast<uint4*>(mask + ((size_t)slot * H + ty0) * W)[c] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+      return;
+    }
     if (y < H)
       for (int x = tx; x < W; x += 32) {
         if (warped) warped[orow + x] = __ldg(&src[(size_t)y * W + x]);
@@ -174,9 +183,18 @@ warp_batch_kernel(const float* __restrict__ images, const float* __restrict__ ai
   for (int t = threadIdx.x; t < tiles_x; t += blockDim.x) cls_s[t] = (uint8_t)classify_tile(m, g, ek, t * kTileW, ty0, H, W);
   const float yn = y < H ? __ldg(&g.ys[y]) : 0.f;
   __syncthreads();
+  if (vec)
+    for (int c = threadIdx.x; c < block_rows * chunks_per_row; c += blockDim.x) {
+      const int r = c / chunks_per_row, xc = c - r * chunks_per_row;
+      const int cls = cls_s[xc >> 1];  // a 16-pixel chunk lies inside one 32-pixel tile
+      if (cls == kTileMixed) continue;
+      const uint32_t v = cls == kTileOutside ? 0u : 0x01010101u;
+      reinterpret_cast<uint4*>(mask + ((size_t)slot * H + ty0) * W)[c] = make_uint4(v, v, v, v);
+    }
   int nmixed = 0;
   for (int t = 0; t < tiles_x; ++t) {
     const int cls = cls_s[t];  // block-uniform
+    if (vec && cls != kTileMixed) continue;
     const int tx0 = t * kTileW, x = tx0 + tx;
     const bool in_img = x < W && y < H;
     if (cls == kTileOutside) {

@@ -63,7 +63,8 @@ struct spn_ctx {
   int opt_fuse_front = 1;   // warp + block_1 + block_2 in one kernel (front_tc.cu)
   int opt_fuse_head = 1;    // convPb + softmax + depth-to-space in one kernel (head_tc.cu)
   int opt_pdl = 1;          // programmatic dependent launch along the tensor-core chain
-  int opt_front_variant = 0;  // diagnostic build only (tools/front_dbg.cu)
+  int opt_front_variant = 0;  // diagnostic build only (tools/front_probe.py)
+  int opt_front_pair = 0;   // fused front end as a 2-CTA cluster with cta_group::2 MMAs (front2_tc.cu)
 };
 
 void spn_set_error(const char* fmt, ...);
@@ -163,6 +164,8 @@ int spn_tc_encoder_slots(spn_ctx* ctx, const float* d_images, const float* d_hin
                          int H, int W, int mode, cudaStream_t s);
 int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots, int H,
                         int W, int mode, const void* w1img, void* d_out, cudaStream_t s);
+int spn_front2_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots, int H,
+                         int W, int mode, const void* w1img, void* d_out, cudaStream_t s);
 float* spn_tc_logits_scratch(spn_ctx* ctx, int B, int H, int W);
 int spn_tc_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_in, int B, int H, int W, bool relu, bool pool,
                       float* d_out, cudaStream_t s);

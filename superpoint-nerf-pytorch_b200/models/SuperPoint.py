@@ -5,8 +5,10 @@ The nn.Conv2d / nn.BatchNorm2d sub-modules only *hold* the parameters (so ``stat
 ``load_state_dict`` / ``.to`` behave like the reference, engine.py:108-117); forward never calls them.
 Inference only (the reference's export tasks call ``model.eval()``, export.py:21): BN uses running stats.
 
-Extension keys (all optional) in the ``model`` config: ``precision`` in {'fp32','f16','bf16'} (default from
-$SPN_B200_PRECISION, else 'fp32'), ``dense_desc`` (default True, as the reference), ``keypoints`` (default False): add
+Extension keys (all optional) in the ``model`` config: ``precision`` in {'f16','fp32','bf16'} (default from
+$SPN_B200_PRECISION, else 'f16': tcgen05 convolutions on fp16 operands with fp32 accumulation - the same 10-bit mantissa
+as the TF32 convolutions the reference itself runs on any Ampere+ GPU, parity gate 5e-3 / >= 99 % keypoints, tested on
+the export workload; 'fp32' selects the strict FFMA path with the 1e-4 gate), ``dense_desc`` (default True, as the reference), ``keypoints`` (default False): add
 ``detector_output['keypoints']`` (B,max_kp,2) int32 (row, col; row-major order like torch.nonzero of prob_heatmap_nms),
 ``detector_output['keypoint_count']`` (B,) and ``descriptor_output['desc_sparse']`` (B,max_kp,256) = desc[:, y, x] at the
 keypoints - computed by ONE C-ABI call (spn_detect_describe: NMS once, no dense 315 MB descriptor map unless
@@ -68,7 +70,7 @@ class SuperPoint(nn.Module):
             if list(config["descriptor_head"]["descriptor_dim"]) != [128, 256] or config["descriptor_head"]["grid_size"] != 8:
                 raise ValueError("only descriptor_dim [128,256] / grid_size 8 is supported")
             self.descriptor_head = _DescriptorHead(config["descriptor_head"])
-        prec = config.get("precision", os.environ.get("SPN_B200_PRECISION", "fp32"))
+        prec = config.get("precision", os.environ.get("SPN_B200_PRECISION", "f16"))
         if prec not in MODES:
             raise ValueError(f"precision must be one of {sorted(MODES)}, got {prec!r}")
         self.mode = MODES[prec]
