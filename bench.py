@@ -341,7 +341,8 @@ def run_native(args):
     kernels = [tensor_entry(n) for n in LAYER_FLOPS]
     # fast modes: the image warp is fused into front_tc_kernel, warp_batch only writes the 1-byte validity masks;
     # strict fp32 mode: it also reads the image and writes the warped copy (614.4 KB / homography)
-    warp_bytes = NUM_H * H * W if args.precision != "fp32" else (NUM_H - 1) * 4 * H * W * 2 + NUM_H * H * W
+    fused_warp = args.precision in ("f16", "bf16")
+    warp_bytes = NUM_H * H * W if fused_warp else (NUM_H - 1) * 4 * H * W * 2 + NUM_H * H * W
     kernels += [hbm_entry("warp_batch", imgs_rank * warp_bytes),
                 hbm_entry("ha_aggregate", imgs_rank * (NUM_H * 4 * H * W + 4 * H * W)),              # 30.7 MB read + 307 KB written / image
                 hbm_entry("softmax_d2s", imgs_rank * NUM_H * (65 * (H // 8) * (W // 8) * 4 + 4 * H * W)),
@@ -351,22 +352,23 @@ def run_native(args):
     total_kernel_ms = sum(t for t, _ in prof.values())
     roof = None
     if dom:
-        tpf = ncu_block2_traffic_per_forward() if args.precision != "fp32" else None
+        tpf = ncu_block2_traffic_per_forward() if fused_warp else None
         fwd_per_launch = forwards / max(dom["launches"], 1)
         roof = {"bound": "tensor", "achieved": dom["achieved"], "peak": dom["peak"], "unit": "TFLOP/s", "frac": dom["frac"],
                 "traffic": (tpf * fwd_per_launch) if tpf else None, "traffic_unit": "bytes per launch (ncu dram read+write)",
                 "algorithmic_flops_per_launch": (LAYER_FLOPS["backbone.block_2"] + (LAYER_FLOPS["backbone.block_1"]
                                                  if "backbone.block_1" not in prof else 0.0)) * fwd_per_launch,
                 "ms_per_launch": dom["ms_per_launch"], "kernel": ("front_tc_kernel = homography warp + block_1 (1->64) + block_2 (64->64, ReLU, 2x2 pool) fused; implicit GEMM "
-                           "M=pixels N=64 K=576 (+K=16 for block_1) @240x320") if args.precision != "fp32" else
-                          "conv_fp32_kernel block_2 (strict FFMA path; tensor peak shown for scale only)",
+                           "M=pixels N=64 K=576 (+K=16 for block_1) @240x320") if fused_warp else
+                          ("conv_split_fold_kernel<64> block_2 (fp16 hi/lo split: 3 MMAs per product, so the useful-FLOP rate tops out at a third of the tensor peak)"
+                           if args.precision == "f16x3" else "conv_fp32_kernel block_2 (strict FFMA path; tensor peak shown for scale only)"),
                 "peak_source": f"{pk_kind} bf16_tflops_sustained", "share_of_step": (prof["backbone.block_2"][0] / total_kernel_ms)
                 if total_kernel_ms else None}
     line = {"metric": "pseudo-label img/s (240x320, 100 H)", "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "ms_per_step_instrumented": ms_instr / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "f16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "f16": "f16", "bf16": "bf16", "f16x3": "f16x3 (fp16 hi/lo split, fp32-grade)"}[args.precision], "data": "synthetic",
             "config": {"workload": "MagicPoint HA pseudo-label export, 240x320, 100 homographies (configs[1])",
                        "images_per_step_per_gpu": ips, "forwards_per_step_per_gpu": ips * NUM_H, "precision": args.precision,
                        "weights": "random-init", "sampler": "device", "streams": args.streams, "parallelism": f"image-sharded x{world}",
@@ -400,7 +402,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SPN_B200_PRECISION", "f16"), choices=["fp32", "f16", "bf16"],
+    ap.add_argument("--precision", default=os.environ.get("SPN_B200_PRECISION", "f16"), choices=["fp32", "f16", "bf16", "f16x3"],
                     help="f16 (default): tcgen05 convolutions, fp16 operands / fp32 accumulate, 5e-3 parity gate; "
                          "fp32: strict FFMA convolutions, 1e-4 parity gate")
     ap.add_argument("--images-per-step", type=int, default=128,

@@ -50,7 +50,9 @@ enum {
 enum {
   SPN_MODE_FP32 = 0, /* strict: fp32 FFMA convolutions (1e-4 parity gate)                       */
   SPN_MODE_F16 = 1,  /* fast: tcgen05 implicit GEMM, fp16 operands, fp32 accumulate (5e-3 gate) */
-  SPN_MODE_BF16 = 2  /* fast: tcgen05 implicit GEMM, bf16 operands, fp32 accumulate             */
+  SPN_MODE_BF16 = 2, /* fast: tcgen05 implicit GEMM, bf16 operands, fp32 accumulate             */
+  SPN_MODE_F16X3 = 3 /* strict on the tensor cores: activations and weights split into fp16 (hi, lo) pairs, three
+                        tcgen05 MMAs per product (hi.hi + hi.lo + lo.hi), fp32 accumulate (1e-4 parity gate)  */
 };
 
 SPN_API const char* spn_last_error(void);

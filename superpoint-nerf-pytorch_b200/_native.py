@@ -11,8 +11,8 @@ import torch
 _HERE = Path(__file__).resolve().parent
 _LIB_PATH = _HERE / "libspn_b200.so"
 
-MODE_FP32, MODE_F16, MODE_BF16 = 0, 1, 2
-MODES = {"fp32": MODE_FP32, "f16": MODE_F16, "fp16": MODE_F16, "bf16": MODE_BF16}
+MODE_FP32, MODE_F16, MODE_BF16, MODE_F16X3 = 0, 1, 2, 3
+MODES = {"fp32": MODE_FP32, "f16": MODE_F16, "fp16": MODE_F16, "bf16": MODE_BF16, "f16x3": MODE_F16X3, "strict_tc": MODE_F16X3}
 
 LAYER_PREFIXES = [
     "backbone.block_1", "backbone.block_2", "backbone.block_3", "backbone.block_4",

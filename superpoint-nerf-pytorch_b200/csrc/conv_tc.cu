@@ -470,6 +470,8 @@ TcPlan tc_plan(int B, int H, int W) {
 
 }  // namespace
 
+const float* spn_tc_block1_weights(spn_ctx* ctx) { return tc_state(ctx)->w1; }
+
 int spn_tc_pack_layer(spn_ctx* ctx, int layer, const float* h_wfold, const float* h_bfold, cudaStream_t s) {
   TcState* st = tc_state(ctx);
   SpnLayer& L = ctx->layers[layer];

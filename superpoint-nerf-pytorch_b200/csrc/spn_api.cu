@@ -76,6 +76,7 @@ extern "C" int spn_destroy(spn_ctx* ctx) {
     if (L.bias) cudaFree(L.bias);
     for (auto& p : L.w16) if (p) cudaFree(p);
     for (auto& p : L.w16f) if (p) cudaFree(p);
+    if (L.w16x) cudaFree(L.w16x);
   }
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->aux) cudaFree(ctx->aux);
@@ -156,7 +157,9 @@ extern "C" int spn_pack_weights(spn_ctx* ctx, int layer, const float* h_w, const
   SPN_CUDA(cudaMemcpy(L.bias, bpk.data(), bpk.size() * sizeof(float), cudaMemcpyHostToDevice));
   L.cin = cin; L.cout = cout; L.ks = ksize; L.cout_pad = cout_pad;
   ctx->feat_mode = -1;
-  return spn_tc_pack_layer(ctx, layer, wf.data(), bf.data(), s);
+  int rc = spn_tc_pack_layer(ctx, layer, wf.data(), bf.data(), s);
+  if (rc) return rc;
+  return spn_split_pack_layer(ctx, layer, wf.data(), bf.data());
 }
 
 // workspace carve-up for the strict (NCHW fp32) path, in floats
@@ -190,6 +193,9 @@ extern "C" int spn_encoder_forward(spn_ctx* ctx, const float* d_images, int B, i
     if (!ctx->layers[l].w32) { spn_set_error("spn_encoder_forward: layer %d has no weights", l); return SPN_E_STATE; }
   if (mode == SPN_MODE_F16 || mode == SPN_MODE_BF16) {
     rc = spn_tc_encoder(ctx, d_images, B, H, W, mode, s);
+    if (rc) return rc;
+  } else if (mode == SPN_MODE_F16X3) {
+    rc = spn_split_encoder(ctx, d_images, B, H, W, s);
     if (rc) return rc;
   } else {
     SPN_REQUIRE(mode == SPN_MODE_FP32, "spn_encoder_forward: unknown mode %d", mode);
@@ -255,7 +261,10 @@ extern "C" int spn_detector_head_forward(spn_ctx* ctx, int B, int H, int W, int 
   SPN_REQUIRE(Pb.cout == 65, "detector head must have 65 output channels (grid_size 8), got %d", Pb.cout);
   const int Hc = H / 8, Wc = W / 8;
   float* logits = d_logits;
-  if (mode == SPN_MODE_FP32) {
+  if (mode == SPN_MODE_F16X3) {
+    if (!logits) logits = spn_split_logits_scratch(ctx, B, H, W);
+    if ((rc = spn_split_head(ctx, SPN_L_CONVPA, SPN_L_CONVPB, B, H, W, logits, s))) return rc;
+  } else if (mode == SPN_MODE_FP32) {
     const Fp32Plan p = fp32_plan(B, H, W);
     float* A = (float*)ctx->ws;
     if (!logits) logits = A + p.bufA + p.bufB + p.feat;
@@ -282,6 +291,7 @@ extern "C" int spn_descriptor_head_forward(spn_ctx* ctx, int B, int H, int W, in
     return SPN_E_STATE;
   }
   const int Hc = H / 8, Wc = W / 8;
+  if (mode == SPN_MODE_F16X3) return spn_split_head(ctx, SPN_L_CONVDA, SPN_L_CONVDB, B, H, W, d_desc_raw, s);
   if (mode == SPN_MODE_FP32) {
     float* A = (float*)ctx->ws;
     if ((rc = spn_conv_fp32(ctx, SPN_L_CONVDA, (const float*)ctx->feat, A, B, Hc, Wc, true, false, s))) return rc;
@@ -300,6 +310,7 @@ extern "C" int spn_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_
   SpnDeviceGuard guard(ctx->device);
   ctx->feat_mode = -1;  // the workspace is reused
   if (mode == SPN_MODE_FP32 || ctx->layers[layer].cin % 64 != 0) return spn_conv_fp32(ctx, layer, d_in, d_out, B, H, W, relu != 0, pool != 0, s);
+  if (mode == SPN_MODE_F16X3) return spn_split_conv_layer(ctx, layer, d_in, B, H, W, relu != 0, pool != 0, d_out, s);
   SPN_REQUIRE(mode == SPN_MODE_F16 || mode == SPN_MODE_BF16, "spn_conv_layer: unknown mode %d", mode);
   return spn_tc_conv_layer(ctx, layer, mode, d_in, B, H, W, relu != 0, pool != 0, d_out, s);
 }

@@ -17,6 +17,7 @@ struct SpnLayer {
   float* bias = nullptr;   // [cout_pad] fp32, BN folded
   void* w16[2] = {nullptr, nullptr};  // tcgen05 operand-B images (fp16, bf16), see conv_tc.cu
   void* w16f[2] = {nullptr, nullptr}; // same for the kx-folded 3x3 kernel (N = 192), see conv_fold.cu
+  void* w16x = nullptr;               // (hi, lo) fp16 operand-B images of the split strict mode, see conv_split.cu
 };
 
 struct SpnProfRec {
@@ -166,6 +167,13 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
                         int W, int mode, const void* w1img, void* d_out, cudaStream_t s);
 int spn_front2_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv, int n_h, int slot_begin, int n_slots, int H,
                          int W, int mode, const void* w1img, void* d_out, cudaStream_t s);
+// split strict mode on the tensor cores (conv_split.cu)
+int spn_split_pack_layer(spn_ctx* ctx, int layer, const float* w, const float* b);
+int spn_split_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, cudaStream_t s);
+int spn_split_head(spn_ctx* ctx, int layer_a, int layer_b, int B, int H, int W, float* d_out, cudaStream_t s);
+float* spn_split_logits_scratch(spn_ctx* ctx, int B, int H, int W);
+int spn_split_conv_layer(spn_ctx* ctx, int layer, const float* d_in, int B, int H, int W, bool relu, bool pool, float* d_out, cudaStream_t s);
+const float* spn_tc_block1_weights(spn_ctx* ctx);
 float* spn_tc_logits_scratch(spn_ctx* ctx, int B, int H, int W);
 int spn_tc_conv_layer(spn_ctx* ctx, int layer, int mode, const float* d_in, int B, int H, int W, bool relu, bool pool,
                       float* d_out, cudaStream_t s);

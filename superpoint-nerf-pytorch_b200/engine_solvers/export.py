@@ -135,7 +135,7 @@ class HomographyAdaptation:
         if homographies is None:
             homographies = self._homographies(NI, n_h, H, W, first_index)
         h, hinv, fwd, hback = self._sampling_matrices(ctx, homographies, NI, n_h, H, W, imgs.device)   # export.py:49 + kornia
-        fused = self.model.mode != 0 and self.ha.get("fused_warp", True)         # tensor-core modes: warp inside conv kernel
+        fused = self.model.mode in (1, 2) and self.ha.get("fused_warp", True)    # 16-bit modes: warp inside the first conv kernel
         warped, mask = ctx.warp_batch(imgs, fwd, self.ha["valid_border_margin"], want_warped=not fused)  # export.py:51-66
         B = NI * (n_h + 1)
         probs = torch.empty((B, H, W), dtype=torch.float32, device=imgs.device)

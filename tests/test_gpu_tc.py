@@ -247,3 +247,81 @@ def test_fast_path_is_deterministic_across_chunkings():
             outs.append(heat.clone())
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
+
+
+# ------------------------------------------------------------------------------------------------ strict mode on the tensor cores
+STRICT = 1e-4
+
+
+@pytest.mark.parametrize("name,shape", [
+    ("backbone.block_2", (2, 64, 48, 40)), ("backbone.block_3", (1, 64, 32, 24)), ("backbone.block_5", (2, 64, 30, 40)),
+    ("backbone.block_6", (1, 128, 60, 80)), ("backbone.block_8", (3, 128, 30, 40)), ("detector_head.convPa", (2, 128, 30, 40)),
+    ("detector_head.convPb", (2, 256, 30, 40)), ("descriptor_head.convDb", (1, 256, 15, 20)), ("backbone.block_2", (1, 64, 240, 320)),
+    ("backbone.block_7", (1, 128, 5, 6)), ("descriptor_head.convDa", (1, 128, 16, 24))])
+def test_split_conv_layer_vs_fp32_oracle(sp_model, name, shape):
+    """SPN_MODE_F16X3 (fp16 hi/lo split of activations and weights, three tcgen05 MMAs per product) against the fp32
+    oracle of VGG_Block.forward on UNROUNDED inputs: the strict 1e-4 gate, layer by layer (both fold widths, the 1x1
+    heads, ragged sizes, pooled and unpooled)."""
+    m, sd = sp_model
+    ctx = m.native()
+    lid = LAYER_ID[name]
+    _n, cin, cout, k, relu, pool = O.layer_table(superpoint=True)[lid]
+    if shape[2] % 2 or shape[3] % 2:
+        pool = False
+    rng = np.random.RandomState(lid + 7)
+    x = torch.from_numpy((np.maximum(rng.randn(*shape), 0) * rng.uniform(0.01, 3.0, size=(1, shape[1], 1, 1))).astype(np.float32))
+    want = O.vgg_block(sd, name, x, k, relu, pool).numpy()
+    got = ctx.conv_layer(lid, x.cuda(), 3, relu=relu, pool=pool, cout=cout).cpu().numpy()
+    assert got.shape == want.shape
+    err = rel_err(got, want)
+    print(f"f16x3 {name} {shape}: rel err {err:.2e}")
+    assert err < 2e-5, f"{name} {shape}: rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(2, 240, 320), (1, 480, 640), (3, 120, 160), (1, 64, 72)])
+def test_split_forward_vs_oracle_strict_gate(shape):
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    B, H, W = shape
+    sd = O.make_state_dict("superpoint", seed=21, logit_gain=6.0)
+    c = dict(copy.deepcopy(SP_MODEL), precision="f16x3", dense_desc=False)
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    x = torch.from_numpy(np.stack([smooth_image(H, W, 40 + i) for i in range(B)])[:, None])
+    want = O.model_forward(sd, x, SP_MODEL, dense_desc=False)
+    got = m(x.cuda())
+    e1 = rel_err(got["detector_output"]["logits"].cpu().numpy(), want["detector_output"]["logits"].numpy())
+    e2 = rel_err(got["detector_output"]["prob_heatmap"].cpu().numpy(), want["detector_output"]["prob_heatmap"].numpy())
+    e3 = rel_err(got["descriptor_output"]["desc_raw"].cpu().numpy(), want["descriptor_output"]["desc_raw"].numpy())
+    print(f"f16x3 {shape}: logits {e1:.2e} prob {e2:.2e} desc_raw {e3:.2e}")
+    assert e1 < STRICT and e2 < STRICT and e3 < STRICT, (e1, e2, e3)
+
+
+def test_split_mode_ha_export_vs_golden_and_oracle(golden):
+    """The homography-adaptation export in f16x3: the reference's golden aggregate at 1e-4 over all pixels and >= 99 %
+    keypoints, and the 240x320 / 25-homography random-init headline workload against the oracle."""
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import HomographyAdaptation
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    g = golden("ha_export.npz")
+    sd = O.make_state_dict("magicpoint", seed=int(g["seed"]), logit_gain=float(g["gain"]))
+    c = dict(copy.deepcopy(MP_MODEL), precision="f16x3")
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(sd)
+    eng = HomographyAdaptation({"homography_adaptation": copy.deepcopy(HA_CFG), "model": c}, m, "cuda")
+    heat, _ = eng.heatmaps(torch.from_numpy(g["image"]).cuda(), homographies=torch.from_numpy(g["H"]).view(1, 7, 3, 3))
+    err = rel_err(heat[0].cpu().numpy(), g["agg"])
+    a, b = keypoint_agreement(eng.keypoints(heat)[0], g["keypoints"])
+    print(f"f16x3 HA golden: heatmap rel err {err:.2e}, keypoints {a:.4f}/{b:.4f}")
+    assert err < STRICT and a >= 0.99 and b >= 0.99
+    H, W, n_h = 240, 320, 25
+    sd = _random_init_sd()
+    img = torch.rand((1, 1, H, W), generator=torch.Generator().manual_seed(0))
+    ha = dict(copy.deepcopy(HA_CFG), num=n_h + 1)
+    np.random.seed(2)
+    want = O.homography_adaptation(sd, img, {"homography_adaptation": ha, "model": copy.deepcopy(MP_MODEL)}, nms_fn=O.box_nms_c)
+    m.load_state_dict(sd)
+    eng = HomographyAdaptation({"homography_adaptation": ha, "model": c}, m, "cuda")
+    heat, _ = eng.heatmaps(img.cuda(), homographies=want["homographies"].view(1, n_h, 3, 3))
+    err = rel_err(heat[0].cpu().numpy(), want["mean_prob"].numpy())
+    a, b = keypoint_agreement(eng.keypoints(heat)[0], want["keypoints"])
+    print(f"f16x3 HA random-init 240x320: heatmap rel err {err:.2e}, keypoints {a:.4f}/{b:.4f}")
+    assert err < STRICT and a >= 0.99 and b >= 0.99
