@@ -234,6 +234,13 @@ SPN_API int spn_mutual_nn_match(spn_ctx* ctx, const float* d_desc1, const int32_
 SPN_API int spn_detector_labels(spn_ctx* ctx, const int32_t* d_kpts_heatmap, const int32_t* d_valid_mask, const float* d_noise,
                                 uint64_t seed, int B, int H, int W, int64_t* d_labels, float* d_valid_cells, spn_stream stream);
 
+/* ExportNeRFDetections.step splat (engine_solvers/export.py:271-283): for every pair i in order, the 3x3 patch of
+ * d_prob_src [H][W] around the source point d_src_pts[i] (int32 row, col) is copied onto the 3x3 patch of d_out [H][W]
+ * around int(d_dst_pts[i]) (fp32 row, col) - a single pixel if either point is within one pixel of the border; later
+ * pairs overwrite earlier ones, everything else is 0. */
+SPN_API int spn_nerf_splat(spn_ctx* ctx, const float* d_prob_src, const float* d_dst_pts, const int32_t* d_src_pts, int n_pairs, int H,
+                           int W, float* d_out, spn_stream stream);
+
 /* Per-kernel CUDA-event timing for bench.py's roofline leg.  Slots 0..11 = the convolution of layer SPN_L_*,
  * then the bandwidth-bound kernels.  spn_profile_read synchronises, writes the accumulated milliseconds and launch
  * counts per slot into HOST arrays of SPN_PROF_SLOTS entries and resets the counters. */

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "spn_repeatability_counts": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, C.c_double, _vp, _vp]),
     "spn_mutual_nn_match": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "spn_detector_labels": (_i, [_vp, _vp, _vp, _vp, C.c_uint64, _i, _i, _i, _vp, _vp, _vp]),
+    "spn_nerf_splat": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "spn_launch_count": (C.c_int64, [_vp]),
     "spn_profile_enable": (_i, [_vp, _i]),
     "spn_profile_read": (_i, [_vp, _vp, _vp]),
@@ -377,6 +378,21 @@ class Context:
         self._call("spn_detector_labels", self.handle, _ptr(kpts_heatmap), _ptr(valid_mask), _ptr(noise), C.c_uint64(seed), B, H, W,
                    _ptr(labels), _ptr(cells), self._s())
         return labels, cells
+
+    def nerf_splat(self, prob_src, dst_pts, src_pts):
+        """ExportNeRFDetections.step splat: prob_src (H,W) fp32, dst_pts (n,2) fp32, src_pts (n,2) int32 -> (H,W) fp32."""
+        prob_src = _dense(prob_src)
+        _chk_dev(prob_src, torch.float32, "prob_src", self.device)
+        H, W = prob_src.shape
+        n = int(dst_pts.shape[0])
+        if n:
+            dst_pts, src_pts = _dense(dst_pts), _dense(src_pts)
+            _chk_dev(dst_pts, torch.float32, "dst_pts", self.device)
+            _chk_dev(src_pts, torch.int32, "src_pts", self.device)
+        out = torch.empty((H, W), dtype=torch.float32, device=prob_src.device)
+        self._call("spn_nerf_splat", self.handle, _ptr(prob_src), _ptr(dst_pts) if n else None, _ptr(src_pts) if n else None, n, H, W,
+                   _ptr(out), self._s())
+        return out
 
     # ---- on-GPU evaluation (evaluations/*.py of the reference) -----------------------------------
     SELECT_CAP = 16384

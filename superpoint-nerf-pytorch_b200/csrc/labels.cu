@@ -62,3 +62,67 @@ extern "C" int spn_detector_labels(spn_ctx* ctx, const int32_t* d_kpts_heatmap, 
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// ExportNeRFDetections.step splat (engine_solvers/export.py:271-283 of the reference): for every (destination point u_i,
+// source point w_i) pair IN ORDER, copy the 3x3 patch of the source heatmap around w_i onto the 3x3 patch around u_i
+// (a single pixel when either point is within one pixel of the border); later pairs overwrite earlier ones.  The
+// sequential "last writer wins" rule is reproduced in parallel with an owner map: pass 1 records, per destination
+// pixel, the highest pair index that covers it (atomicMax), pass 2 gathers the value that pair would have written.
+namespace {
+
+__device__ __forceinline__ bool nerf_border(int u0, int u1, int w0, int w1, int H, int W) {
+  return u0 <= 1 || u1 <= 1 || u0 >= H - 1 || u1 >= W - 1 || w0 <= 1 || w1 <= 1 || w0 >= H - 1 || w1 >= W - 1;
+}
+
+__global__ void nerf_owner_kernel(const float* __restrict__ dst, const int32_t* __restrict__ src, int n, int H, int W,
+                                  unsigned* __restrict__ owner) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int u0 = (int)dst[2 * i], u1 = (int)dst[2 * i + 1];   // python int(): truncation toward zero
+  const int w0 = src[2 * i], w1 = src[2 * i + 1];
+  if (u0 < 0 || u0 >= H || u1 < 0 || u1 >= W) return;
+  if (nerf_border(u0, u1, w0, w1, H, W)) {
+    atomicMax(&owner[u0 * W + u1], (unsigned)i + 1u);
+  } else {
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) atomicMax(&owner[(u0 + dy) * W + u1 + dx], (unsigned)i + 1u);
+  }
+}
+
+__global__ void nerf_gather_kernel(const float* __restrict__ prob, const float* __restrict__ dst, const int32_t* __restrict__ src, int H,
+                                   int W, const unsigned* __restrict__ owner, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  const unsigned o = owner[p];
+  float v = 0.f;
+  if (o) {
+    const int i = (int)o - 1;
+    const int u0 = (int)dst[2 * i], u1 = (int)dst[2 * i + 1];
+    const int w0 = src[2 * i], w1 = src[2 * i + 1];
+    const int y = p / W, x = p - y * W;
+    v = prob[(w0 + (y - u0)) * W + w1 + (x - u1)];   // (y - u0, x - u1) is (0, 0) in the single-pixel case
+  }
+  out[p] = v;
+}
+
+}  // namespace
+
+extern "C" int spn_nerf_splat(spn_ctx* ctx, const float* d_prob_src, const float* d_dst_pts, const int32_t* d_src_pts, int n_pairs, int H,
+                              int W, float* d_out, spn_stream stream) {
+  SPN_REQUIRE(ctx && d_prob_src && d_out && (n_pairs == 0 || (d_dst_pts && d_src_pts)), "spn_nerf_splat: null pointer");
+  SPN_REQUIRE(n_pairs >= 0 && H > 2 && W > 2, "spn_nerf_splat: bad shape");
+  SpnDeviceGuard guard(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = spn_ensure_aux(ctx, (size_t)H * W * sizeof(unsigned), s);
+  if (rc) return rc;
+  unsigned* owner = (unsigned*)ctx->aux;
+  SPN_CUDA(cudaMemsetAsync(owner, 0, (size_t)H * W * sizeof(unsigned), s));
+  if (n_pairs) {
+    nerf_owner_kernel<<<spn_cdiv(n_pairs, 128), 128, 0, s>>>(d_dst_pts, d_src_pts, n_pairs, H, W, owner);
+    SPN_CHECK_LAUNCH(ctx);
+  }
+  nerf_gather_kernel<<<spn_cdiv(H * W, 256), 256, 0, s>>>(d_prob_src, d_dst_pts, d_src_pts, H, W, owner, d_out);
+  SPN_CHECK_LAUNCH(ctx);
+  return SPN_OK;
+}

@@ -141,7 +141,8 @@ def main(config_path: str,
         synthetic: feed this many synthetic images instead of the dataset loader.
         random_init: skip loading `pretrained` (benchmarking with random-init weights).
     """
-    if task in ("train", "export_NeRF_labels"):
+    if task in ("train", "export_NeRF_labels"):   # ExportNeRFDetections is available as a class (engine_solvers/export.py); the NeRF
+        # dataset loader that feeds it is not part of this package
         raise SystemExit(f"task {task!r} is outside the B200 hot path (SURVEY.md section 8); use the reference for it")
     with open(config_path, "r") as f:
         config = yaml.safe_load(f)

@@ -410,6 +410,75 @@ class Export_Hpatches_Descriptors:
             writer.close()
 
 
+class ExportNeRFDetections:
+    """NeRF multi-view pseudo-labels with the reference's class interface (engine_solvers/export.py:225-366): for every
+    view j of a batch, the heatmap of j is averaged with the heatmaps of ~75 % of the other views k, re-projected into j
+    through the depth maps and camera poses (3x3 patches around k's detections), then box_nms + threshold + nonzero ->
+    ``<EXPER_PATH>/outputs/<experiment>/<split>/<name>.npy``.
+
+    What changes underneath: the reference runs the model once per (j, k) pair; here every view is forwarded ONCE through
+    the one-call path (heatmap + NMS + keypoint list, spn_detect_describe), the sequential 3x3 patch copies of
+    export.py:271-283 are one order-preserving kernel (spn_nerf_splat) and the final NMS is the bit-exact box_nms kernel.
+    The pairing quirk of export.py:269-271 (the border filter shortens ``unwarped_pts`` but the loop zips it with the
+    unfiltered ``warped_pts``) is reproduced as is."""
+
+    def __init__(self, config, model, dataloader, split, device):
+        self.config = config
+        self.model = model.eval()
+        self.dataloader = dataloader
+        self.split = split
+        self.device = device
+        self.output_dir = Path(settings.EXPER_PATH, "outputs", self.config["data"]["experiment_name"], self.split)
+        os.makedirs(self.output_dir, exist_ok=True)
+        self.export_NeRF()
+
+    @torch.no_grad()
+    def reproject(self, prob_k, pts_k, depth_k, intrinsics, rot_k, trans_k, rot_j, trans_j):
+        """One ExportNeRFDetections.step without the model call: view k's detections splatted into view j's frame."""
+        from ..data.data_utils.kp_utils import filter_points, warp_points_NeRF
+        ctx = self.model.native()
+        H, W = prob_k.shape
+        if len(pts_k) == 0:
+            return torch.zeros_like(prob_k)
+        unwarped = warp_points_NeRF(pts_k.to(torch.float32), depth_k.unsqueeze(0), intrinsics.unsqueeze(0), rot_k.unsqueeze(0),
+                                    trans_k.unsqueeze(0), rot_j.unsqueeze(0), trans_j.unsqueeze(0), self.device)
+        unwarped = filter_points(unwarped.reshape(-1, 2), (H, W), self.device)
+        n = len(unwarped)
+        return ctx.nerf_splat(prob_k, unwarped.to(torch.float32).contiguous(), pts_k[:n].contiguous())
+
+    @torch.no_grad()
+    def export_NeRF(self):
+        import random
+        dh = self.config["model"]["detector_head"]
+        for _, data in enumerate(tqdm(self.dataloader, desc="Exporting NeRF Labels", colour="green")):
+            data = move_to_device(data, self.device)
+            names = data["name"]
+            todo = [j for j in range(len(names)) if not Path(self.output_dir, f"{names[j]}.npy").exists()]
+            if not todo:
+                continue
+            out = self.model(data["raw"]["image"], keypoints=True)["detector_output"]      # every view forwarded once
+            prob, kp, cnt = out["prob_heatmap"], out["keypoints"], out["keypoint_count"].cpu().numpy()
+            if cnt.max(initial=0) > kp.shape[1]:
+                raise RuntimeError("keypoint list overflow: set detector_head.top_k")
+            for j in range(len(names)):
+                save_path = Path(self.output_dir, f"{names[j]}.npy")
+                if save_path.exists():
+                    continue
+                other_index = [k for k in range(len(names)) if k != j]
+                other_index = random.choices(other_index, k=int(0.75 * len(other_index)))     # export.py:320-321, python's RNG
+                maps = [prob[j]]
+                for k in other_index:
+                    maps.append(self.reproject(prob[k], kp[k, :cnt[k]], data["raw"]["input_depth"][k], data["camera_intrinsic_matrix"][j],
+                                               data["raw"]["input_rotation"][k], data["raw"]["input_translation"][k],
+                                               data["raw"]["input_rotation"][j], data["raw"]["input_translation"][j]))
+                mean = torch.stack(maps).sum(0) / float(len(maps))
+                ctx = self.model.native()
+                r = ctx.box_nms(mean.unsqueeze(0), float(dh["nms"]), 0.1, float(dh["det_thresh"]), int(dh["top_k"]),
+                                det_thresh=float(dh["det_thresh"]), want_map=False, max_kp=min(mean.numel(), 16384))
+                n = int(r["kp_count"][0])
+                np.save(save_path, r["kp"][0, :n].cpu().numpy().astype(np.int64))
+
+
 def load_packed_labels(directory):
     """Read every ``packed_rank*.npz`` shard of an ExportDetections run -> {name: (N,2) int64 (row, col)} - the same
     arrays the per-image ``<name>.npy`` files hold (what data/COCO.py:100-102 of the reference loads as labels)."""

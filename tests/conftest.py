@@ -99,3 +99,24 @@ def make_eval_pair(seed, h=96, w=128, n_pts=220):
     desc /= np.linalg.norm(desc, axis=-1, keepdims=True)
     warped_desc /= np.linalg.norm(warped_desc, axis=-1, keepdims=True)
     return {"prob": prob, "warped_prob": warped_prob, "homography": H, "desc": desc, "warped_desc": warped_desc}
+
+
+def make_nerf_batch(seed=0, n_views=4, h=64, w=96):
+    """Synthetic multi-view batch in the layout ExportNeRFDetections consumes (export.py:304-341): images, per-view depth
+    maps with a depth edge, shared intrinsics, small relative rotations / translations.  numpy only (bit-reproducible)."""
+    import torch
+    rng = np.random.RandomState(seed)
+    imgs = np.stack([smooth_image(h, w, 700 + seed * 10 + i) for i in range(n_views)])[:, None]
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    depth = np.stack([2.5 + 0.3 * np.sin(xx / 17.0 + i) + 0.2 * np.cos(yy / 11.0) + 0.5 * (xx > w * (0.45 + 0.05 * i)) for i in range(n_views)])
+    K = np.array([[85.0, 0, w / 2.0], [0, 85.0, h / 2.0], [0, 0, 1.0]], np.float32)
+
+    def rot(ax, ay, az):
+        cx, sx, cy, sy, cz, sz = np.cos(ax), np.sin(ax), np.cos(ay), np.sin(ay), np.cos(az), np.sin(az)
+        return (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+                @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+    R = np.stack([rot(*(rng.uniform(-0.03, 0.03, 3))) for _ in range(n_views)]).astype(np.float32)
+    t = rng.uniform(-0.08, 0.08, (n_views, 3, 1)).astype(np.float32)
+    return {"raw": {"image": torch.from_numpy(imgs.astype(np.float32)), "input_depth": torch.from_numpy(depth.astype(np.float32)),
+                    "input_rotation": torch.from_numpy(R), "input_translation": torch.from_numpy(t)},
+            "camera_intrinsic_matrix": torch.from_numpy(np.stack([K] * n_views)), "name": [f"view{seed}_{i}" for i in range(n_views)]}

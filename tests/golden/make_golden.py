@@ -375,6 +375,28 @@ def main():
               lab_labels=labels9.numpy(), lab_cells=cells9.numpy())
     np.savez_compressed(OUT / "train_reuse.npz", **tr)
 
+    # ---- 10. ExportNeRFDetections (export.py:225-366) on synthetic multi-view batches ---------------------------------
+    import random
+    from conftest import make_nerf_batch
+    nf = {}
+    sdn = O.make_state_dict("magicpoint", seed=13, logit_gain=12.0)
+    mcfg_n = copy.deepcopy(MP_MODEL)
+    mcfg_n["detector_head"]["top_k"] = 300
+    modeln = SuperPoint(copy.deepcopy(mcfg_n)).eval()
+    modeln.load_state_dict(sdn)
+    cfgn = {"data": {"experiment_name": "golden_nerf"}, "model": mcfg_n}
+    batches = [make_nerf_batch(0), make_nerf_batch(1, n_views=5)]
+    random.seed(5)
+    refexport.ExportNeRFDetections(cfgn, modeln, batches, "training", "cpu")
+    for bt in batches:
+        for nm in bt["name"]:
+            nf[nm] = np.load(Path(exper, "outputs", "golden_nerf", "training", f"{nm}.npy"))
+    nf["seed"] = np.array(13)
+    nf["gain"] = np.array(12.0)
+    nf["py_seed"] = np.array(5)
+    np.savez_compressed(OUT / "nerf_export.npz", **nf)
+    print("nerf export keypoints", {k: v.shape for k, v in nf.items() if k.startswith("view")})
+
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

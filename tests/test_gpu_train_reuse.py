@@ -62,3 +62,59 @@ def test_detector_labels_vs_reference(golden):
     picked = torch.gather(torch.cat([k, torch.zeros_like(k[:, :1])], 1), 1, lab2.unsqueeze(1)).squeeze(1)
     assert bool((picked[n_kp > 0] == 1).all())                   # a non-empty cell's label is one of its keypoints
     assert bool((lab2[n_kp <= 1] == labels[n_kp <= 1]).all())
+
+
+def test_nerf_splat_matches_sequential_loop():
+    """spn_nerf_splat vs the reference's sequential Python loop (export.py:271-283) restated in numpy, with overlapping
+    patches (order matters: later pairs overwrite) and border points (single-pixel case)."""
+    import superpoint_nerf_pytorch_b200 as P
+    ctx = P.get_context("cuda:0")
+    rng = np.random.RandomState(4)
+    H, W, n = 48, 64, 400
+    prob = rng.rand(H, W).astype(np.float32)
+    src = np.stack([rng.randint(0, H, n), rng.randint(0, W, n)], 1).astype(np.int32)
+    dst = np.stack([rng.uniform(0, H - 1.001, n), rng.uniform(0, W - 1.001, n)], 1).astype(np.float32)
+    dst[:6] = [[0.2, 5.7], [1.9, 9.0], [H - 1.5, 3.3], [10.5, W - 1.2], [20.0, 20.0], [20.9, 21.2]]
+    want = np.zeros((H, W), np.float32)
+    for u, w_ in zip(dst, src):
+        u0, u1, w0, w1 = int(u[0]), int(u[1]), int(w_[0]), int(w_[1])
+        if u0 <= 1 or u1 <= 1 or u0 >= H - 1 or u1 >= W - 1 or w0 <= 1 or w1 <= 1 or w0 >= H - 1 or w1 >= W - 1:
+            want[u0, u1] = prob[w0, w1]
+        else:
+            want[u0 - 1:u0 + 2, u1 - 1:u1 + 2] = prob[w0 - 1:w0 + 2, w1 - 1:w1 + 2]
+    got = ctx.nerf_splat(torch.from_numpy(prob).cuda(), torch.from_numpy(dst).cuda(), torch.from_numpy(src).cuda()).cpu().numpy()
+    assert np.array_equal(got, want)
+    empty = ctx.nerf_splat(torch.from_numpy(prob).cuda(), torch.zeros((0, 2), device="cuda"), torch.zeros((0, 2), dtype=torch.int32, device="cuda"))
+    assert float(empty.abs().max()) == 0.0
+
+
+def test_export_nerf_detections_vs_reference_golden(golden, tmp_path, monkeypatch):
+    """ExportNeRFDetections on the synthetic multi-view batches of conftest.make_nerf_batch, same python random seed as the
+    reference run that produced the golden keypoint files: >= 99 % of the keypoints within 1 px, both directions."""
+    import copy
+    import random
+    from conftest import MP_MODEL, keypoint_agreement, make_nerf_batch
+    from oracle import spn_oracle as O
+    from superpoint_nerf_pytorch_b200 import settings
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import ExportNeRFDetections
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    g = golden("nerf_export.npz")
+    mcfg = copy.deepcopy(MP_MODEL)
+    mcfg["detector_head"]["top_k"] = 300
+    mcfg["precision"] = "fp32"
+    m = get_model(mcfg, "cuda").eval()
+    m.load_state_dict(O.make_state_dict("magicpoint", seed=int(g["seed"]), logit_gain=float(g["gain"])))
+    monkeypatch.setattr(settings, "EXPER_PATH", str(tmp_path))
+    batches = [make_nerf_batch(0), make_nerf_batch(1, n_views=5)]
+    random.seed(int(g["py_seed"]))
+    ExportNeRFDetections({"data": {"experiment_name": "nerf"}, "model": mcfg}, m, batches, "training", "cuda")
+    worst = 1.0
+    for bt in batches:
+        for nm in bt["name"]:
+            kp = np.load(tmp_path / "outputs" / "nerf" / "training" / f"{nm}.npy")
+            assert kp.dtype == np.int64 and kp.shape[1] == 2
+            a, b = keypoint_agreement(kp, g[nm])
+            worst = min(worst, a, b)
+            assert abs(len(kp) - len(g[nm])) <= max(2, len(g[nm]) // 50), (nm, len(kp), len(g[nm]))
+    print(f"NeRF export: worst keypoint agreement {worst:.4f}")
+    assert worst >= 0.99
