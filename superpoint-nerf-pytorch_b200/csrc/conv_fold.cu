@@ -219,7 +219,7 @@ conv_fold_kernel(const __grid_constant__ CUtensorMap tmap, const FoldParams p) {
                           __shfl_down_sync(0xffffffffu, __uint_as_float(f2[c]), 1);
           const float b = __shfl_up_sync(0xffffffffu, __uint_as_float(f0[c + 1]), 1) + __uint_as_float(f1[c + 1]) +
                           __shfl_down_sync(0xffffffffu, __uint_as_float(f2[c + 1]), 1);
-          h2[(c0 + c) >> 1] = pack2(a, b, p.is_bf16);
+          h2[(c0 + c) >> 1] = p.relu ? pack2_relu(a, b, p.is_bf16) : pack2(a, b, p.is_bf16);   // ReLU commutes with the pool below
         }
       }
       tc_fence_before();
@@ -234,10 +234,6 @@ conv_fold_kernel(const __grid_constant__ CUtensorMap tmap, const FoldParams p) {
         }
         writer = writer && (x & 1) && ((lane >> 4) == 0);
         oy = y >> 1; ox = gx >> 1;
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) h2[c] = max2(h2[c], 0u, p.is_bf16);
       }
       if (writer) {
         uint4* o = reinterpret_cast<uint4*>(p.out);

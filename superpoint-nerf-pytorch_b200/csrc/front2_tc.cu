@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) front2_tc_kernel(const Front2Para
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = c8 * 8 + 2 * e;
-              w[e] = max2(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), p.is_bf16), 0u, p.is_bf16);
+              w[e] = pack2_relu(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), p.is_bf16);
             }
             *reinterpret_cast<uint4*>(slab + (size_t)c8 * kChStride + (size_t)r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
           }
@@ -381,11 +381,11 @@ __global__ void __launch_bounds__(kThreads, 1) front2_tc_kernel(const Front2Para
       mbar_arrive_cta(&bar_d2_empty[acc], 0);
       uint32_t h2[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) h2[c] = pack2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]), p.is_bf16);
+      for (int c = 0; c < 32; ++c) h2[c] = pack2_relu(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]), p.is_bf16);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {  // bias is already in D2; pool first, ReLU after (max commutes)
+      for (int c = 0; c < 32; ++c) {  // bias is already in D2; ReLU was applied by the conversion (it commutes with the pool)
         h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 1), p.is_bf16);
-        h2[c] = max2(max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 8), p.is_bf16), 0u, p.is_bf16);
+        h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 8), p.is_bf16);
       }
       if (live && y < p.H && x < p.W && (g & 1) == 0 && (r & 1) == 0) {
         uint4* o = reinterpret_cast<uint4*>(p.out);

@@ -8,7 +8,8 @@
 //
 // Per CTA tile (8 x 16 output pixels of block_2 before pooling = M 128), pipelined over tiles by warp role:
 //   P  warps 10-17  bilinear-sample the 12 x 20 warped-image patch, build block_1's im2col operand A1
-//                   (256 rows = the 10 x 18 halo pixels (180 used), K = 9 taps padded to 16, fp16) in SMEM
+//                   (256 rows = the 10 x 18 halo pixels (180 used), K = 9 taps padded to 16, fp16) in SMEM;
+//                   two groups of 4 warps, one per tile parity
 //   M  warp 1       MMA1: D1 = A1 . W1 (2 x M128 N64 K16) into TMEM, issued one tile AHEAD of
 //                   MMA2: D2 += slab(tap) . W2(tap) (36 x M128 N64 K16, weights resident in SMEM)
 //   E1 warps 6-9    D1 (bias already added through A1's ones columns, rows outside the image exactly 0 = block_2's
@@ -42,7 +43,7 @@ constexpr int kA1Bytes = 2 * kA1Rows * 16;            // [chunk 2][row 256][8 ha
 constexpr int kStages = 4;
 constexpr int kNA1 = 3;                               // A1 / D1 buffers: MMA1 runs two tiles ahead of MMA2
 constexpr int kThreads = 576;                         // 18 warps
-constexpr int kPThreads = 256;                        // P role: warps 10-17
+constexpr int kPGroup = 128;                          // P role: two groups of 4 warps (10-13, 14-17), one per tile parity
 
 struct FrontParams {
   const float* images;   // [n_src][H][W] fp32
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
     for (int i = 0; i < kNA1; ++i) {
-      mbar_init(&bar_a1_full[i], kPThreads); mbar_init(&bar_a1_empty[i], 1);
+      mbar_init(&bar_a1_full[i], kPGroup); mbar_init(&bar_a1_empty[i], 1);
       mbar_init(&bar_d1_full[i], 1);   mbar_init(&bar_d1_empty[i], 128);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_d2_full[i], 1); mbar_init(&bar_d2_empty[i], 128); }
@@ -192,12 +193,17 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
     }
   } else if (warp >= 10) {
     // ===================== P: warped patch + im2col operand of block_1 =====================
-    const int pt = threadIdx.x - 320;  // 0..255
+    // Two groups of 4 warps, one per tile parity.  A tile's P work is one long dependent chain (coordinates -> four
+    // L2 loads -> interpolation -> patch -> barrier -> im2col rows -> fence), ~2300 cycles when all eight warps work
+    // on the same tile in lock step, which was the slowest stage of the kernel (ncu source page: P never waited for
+    // a free A1 buffer while both MMA issuers spent 39 % of their time waiting for operands).  With the groups
+    // working on alternate tiles each has two tile times per tile and the two samples of a thread overlap their loads.
+    const int grp = (warp - 10) >> 2;
+    const int pt = threadIdx.x - 320 - grp * kPGroup;  // 0..127
     griddep_wait();  // the output buffer may still be read by the previous chunk's kernels; every store follows P's data
     float hm[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     int hm_slot = -1;
-    int i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < n_tiles; t += 2 * gridDim.x, i += 2) {
       const int b = i % kNA1;
       const uint32_t ph = (uint32_t)(i / kNA1) & 1u;
       const int ls = fast_div(t, p.magic_tpi), rr = t - ls * tiles_per_img;
@@ -206,19 +212,23 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       const int src = p.hinv ? slot / (p.n_h + 1) : slot;
       const int j = p.hinv ? slot - src * (p.n_h + 1) : 0;
       const float* img = p.images + (size_t)src * p.H * p.W;
-      mbar_wait(&bar_a1_empty[b], ph ^ 1u);  // MMA1 of tile i-3 has consumed A1[b] (and patch_s[b] long before)
       if (j > 0 && slot != hm_slot) {  // warp-uniform; a CTA's consecutive tiles mostly belong to the same slot
         const float* hp = p.hinv + ((size_t)src * p.n_h + (j - 1)) * 9;
 #pragma unroll
         for (int k = 0; k < 9; ++k) hm[k] = __ldg(hp + k);
         hm_slot = slot;
       }
-      // 1. the 12 x 20 patch of the warped image around the tile (zero outside the frame = block_1's padding)
-      for (int s = pt; s < kQH * kQW; s += kPThreads) {
+      // 1. the 12 x 20 patch of the warped image around the tile (zero outside the frame = block_1's padding):
+      //    two samples per thread, their eight loads in flight together; the values are only stored once A1[b] /
+      //    patch_s[b] are free (MMA1 of tile i-3 has consumed them)
+      float pv[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int s = pt + k * kPGroup;
         const int py = s / kQW, px = s - py * kQW;
         const int y = ty * kTH - 2 + py, x = tx * kTW - 2 + px;
         float v = 0.f;
-        if (y >= 0 && y < p.H && x >= 0 && x < p.W && !(DBG & 1)) {
+        if (s < kQH * kQW && y >= 0 && y < p.H && x >= 0 && x < p.W && !(DBG & 1)) {
           if (j == 0) {
             v = __ldg(&img[(size_t)y * p.W + x]);
           } else {
@@ -227,14 +237,21 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
             v = bilinear_zero_nb(img, sx, sy, p.H, p.W);
           }
         }
-        patch_s[b][s] = to16(v, p.is_bf16);
+        pv[k] = v;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(&bar_a1_empty[b], ph ^ 1u);
+      patch_s[b][pt] = to16(pv[0], p.is_bf16);
+      if (pt + kPGroup < kQH * kQW) patch_s[b][pt + kPGroup] = to16(pv[1], p.is_bf16);
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
       // 2. A1 row r = halo pixel (hy, hx): its 3x3 neighbourhood (K 0..8), then two constant-one columns that
       //    multiply the (hi, lo) bias rows of W1.  Halo pixels outside the image get an all-zero row, so block_1's
       //    output there is exactly 0 = block_2's zero padding.
       const uint32_t one16 = p.is_bf16 ? 0x3F80u : 0x3C00u;
-      for (int r = pt; r < ((DBG & 2) ? 0 : kHalo); r += kPThreads) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int r = pt + k * kPGroup;
+        if (r >= ((DBG & 2) ? 0 : kHalo)) break;
         const int hy = r / kPW, hx = r - hy * kPW;
         const int gy = ty * kTH - 1 + hy, gx = tx * kTW - 1 + hx;
         uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = make_uint4(0u, 0u, 0u, 0u);
@@ -283,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int c = c8 * 8 + 2 * e;
-              w[e] = max2(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), p.is_bf16), 0u, p.is_bf16);
+              w[e] = pack2_relu(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), p.is_bf16);
             }
             *reinterpret_cast<uint4*>(slab + (size_t)c8 * kChStride + (size_t)r * 16) = make_uint4(w[0], w[1], w[2], w[3]);
           }
@@ -320,11 +337,11 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       if (DBG & 32) continue;
       uint32_t h2[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) h2[c] = pack2(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]), p.is_bf16);
+      for (int c = 0; c < 32; ++c) h2[c] = pack2_relu(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]), p.is_bf16);
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {  // bias is already in D2; pool first, ReLU after (max commutes)
+      for (int c = 0; c < 32; ++c) {  // bias is already in D2; ReLU was applied by the conversion (it commutes with the pool)
         h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 1), p.is_bf16);
-        h2[c] = max2(max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 8), p.is_bf16), 0u, p.is_bf16);
+        h2[c] = max2(h2[c], __shfl_xor_sync(0xffffffffu, h2[c], 8), p.is_bf16);
       }
       if (y < p.H && x < p.W && (g & 1) == 0 && (r & 1) == 0 && !(DBG & 16)) {
         uint4* o = reinterpret_cast<uint4*>(p.out);

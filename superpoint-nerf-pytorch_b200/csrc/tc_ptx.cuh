@@ -110,6 +110,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int is_bf16) {
   __half2 t = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// pack with ReLU in the conversion itself (cvt.rn.relu.*x2.f32): one instruction instead of pack + max(x, 0).  ReLU
+// commutes with the max-pool that may follow, so epilogues clamp here and pool afterwards.
+__device__ __forceinline__ uint32_t pack2_relu(float a, float b, int is_bf16) {
+  uint32_t d;
+  if (is_bf16) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b, int is_bf16) {
   if (is_bf16) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
