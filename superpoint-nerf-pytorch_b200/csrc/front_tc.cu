@@ -9,7 +9,7 @@
 // Per CTA tile (8 x 16 output pixels of block_2 before pooling = M 128), pipelined over tiles by warp role:
 //   P  warps 10-17  bilinear-sample the 12 x 20 warped-image patch, build block_1's im2col operand A1
 //                   (256 rows = the 10 x 18 halo pixels (180 used), K = 9 taps padded to 16, fp16) in SMEM;
-//                   two groups of 4 warps, one per tile parity
+//                   kPGroups groups of warps that take tiles round robin
 //   M  warp 1       MMA1: D1 = A1 . W1 (2 x M128 N64 K16) into TMEM, issued one tile AHEAD of
 //                   MMA2: D2 += slab(tap) . W2(tap) (36 x M128 N64 K16, weights resident in SMEM)
 //   E1 warps 6-9    D1 (bias already added through A1's ones columns, rows outside the image exactly 0 = block_2's
@@ -41,9 +41,23 @@ constexpr int kW1Bytes = 2 * 64 * 16;                 // block_1 weights as oper
 constexpr int kA1Rows = 256;
 constexpr int kA1Bytes = 2 * kA1Rows * 16;            // [chunk 2][row 256][8 halfs]
 constexpr int kStages = 4;
-constexpr int kNA1 = 3;                               // A1 / D1 buffers: MMA1 runs two tiles ahead of MMA2
+constexpr int kNA1 = 3;                               // D1 buffers (TMEM): MMA1 runs two tiles ahead of MMA2
 constexpr int kThreads = 576;                         // 18 warps
-constexpr int kPGroup = 128;                          // P role: two groups of 4 warps (10-13, 14-17), one per tile parity
+#ifndef SPN_TURN_TAP
+#define SPN_TURN_TAP 9
+#endif
+constexpr int kTurnTap = SPN_TURN_TAP;               // the issue turn passes to the other issuer after this tap of block_2 (9 = after the bias MMA)
+#ifndef SPN_POLL_NS
+#define SPN_POLL_NS 0
+#endif
+constexpr uint32_t kPollNs = SPN_POLL_NS;             // back-off between barrier polls of the producer / epilogue roles
+#ifndef SPN_P_GROUPS
+#define SPN_P_GROUPS 4
+#endif
+constexpr int kPGroups = SPN_P_GROUPS;                // P role: the 8 warps 10-17 split into groups that take tiles round robin
+constexpr int kPGroup = 256 / kPGroups;               // threads per group
+constexpr int kPSamples = (12 * 20 + kPGroup - 1) / kPGroup, kPRows = (10 * 18 + kPGroup - 1) / kPGroup;   // per thread and tile
+constexpr int kNA1s = kPGroups > 3 ? kPGroups : 3;    // A1 / patch buffers (SMEM)
 
 struct FrontParams {
   const float* images;   // [n_src][H][W] fp32
@@ -51,7 +65,7 @@ struct FrontParams {
   int n_h;               // homographies per source image (slot = src * (n_h + 1) + j, j == 0 is the identity)
   int slot_begin, n_slots;
   int H, W, tiles_x, tiles_y;
-  unsigned long long magic_tpi, magic_tx;   // fast_div magics for tiles_per_img and tiles_x
+  unsigned long long magic_tpi, magic_tx, magic_nh1;   // fast_div magics for tiles_per_img, tiles_x and n_h + 1
   int is_bf16;
   const void* w1img;     // operand-B image of block_1 (taps + bias rows)
   const void* w2img;     // operand-B image of block_2 (72 KB) followed by its 2 KB bias block
@@ -71,34 +85,40 @@ __device__ __forceinline__ uint16_t to16(float v, int bf) {
 template <int DBG>
 __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a1_full[kNA1], bar_a1_empty[kNA1], bar_d1_full[kNA1], bar_d1_empty[kNA1],
-      bar_slab_full[kStages], bar_slab_empty[kStages], bar_d2_full[2], bar_d2_empty[2];
+  __shared__ __align__(8) uint64_t bar_w, bar_a1_full[kNA1s], bar_a1_empty[kNA1s], bar_d1_full[kNA1], bar_d1_empty[kNA1],
+      bar_slab_full[kStages], bar_slab_empty[kStages], bar_d2_full[2], bar_d2_empty[2], bar_turn[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) uint16_t patch_s[kNA1][kQH * kQW];
+  __shared__ __align__(16) uint16_t patch_s[kNA1s][kQH * kQW];
 
   uint8_t* w2s = smem;                                  // 75776
   uint8_t* w1s = smem + kW2Bytes;                       // 2048
-  uint8_t* a1s = w1s + kW1Bytes;                        // kNA1 x 8192   (at 77824)
-  uint8_t* ones = a1s + kNA1 * kA1Bytes;                // 4096          (at 102400)
-  uint8_t* slab0 = ones + kOnesBytes;                   // kStages x 23552  (at 106496 = 104 x 1024)
+  uint8_t* a1s = w1s + kW1Bytes;                        // kNA1s x 8192  (at 77824)
+  uint8_t* ones = a1s + kNA1s * kA1Bytes;               // 4096
+  uint8_t* slab0 = ones + kOnesBytes;                   // kStages x 23552  (1024-aligned: every block above is a multiple of 1 KB... 2 KB)
 
   griddep_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int n_tiles = p.n_slots * tiles_per_img;
 
+  // Shared-memory traffic is a first-order cost here: an M128 x N64 MMA fetches 6 KB of operands per 48 cycles = the
+  // whole 128 B/cycle of the shared-memory pipe, so every other wavefront (st.shared, mbarrier arrivals and polls)
+  // takes its cycle from the MMA stream.  Barriers are therefore arrived on by ONE lane per warp after __syncwarp
+  // (4 arrivals instead of 128 per hand-off).
   if (threadIdx.x == 0) {
     mbar_init(&bar_w, 1);
+    for (int i = 0; i < kNA1s; ++i) { mbar_init(&bar_a1_full[i], kPGroup / 32); mbar_init(&bar_a1_empty[i], 1); }
     for (int i = 0; i < kNA1; ++i) {
-      mbar_init(&bar_a1_full[i], kPGroup); mbar_init(&bar_a1_empty[i], 1);
-      mbar_init(&bar_d1_full[i], 1);   mbar_init(&bar_d1_empty[i], 128);
+      mbar_init(&bar_d1_full[i], 1);   mbar_init(&bar_d1_empty[i], 4);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_d2_full[i], 1); mbar_init(&bar_d2_empty[i], 128); }
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bar_slab_full[i], 128); mbar_init(&bar_slab_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_d2_full[i], 1); mbar_init(&bar_d2_empty[i], 4); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bar_slab_full[i], 4); mbar_init(&bar_slab_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_turn[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_arrive(&bar_turn[0]);  // issuer 0 owns the first turn
   }
   // A1 rows >= 180 are never written again: zero both buffers once
-  for (int i = threadIdx.x; i < kNA1 * kA1Bytes / 16; i += kThreads) reinterpret_cast<uint4*>(a1s)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < kNA1s * kA1Bytes / 16; i += kThreads) reinterpret_cast<uint4*>(a1s)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 1) {  // TMEM: D2 2 x 64 columns + D1 3 buffers x 2 halves x 64 columns = 512 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -143,18 +163,18 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
     const uint32_t d1_col = tmem_base + 128;
 
     auto issue_mma1 = [&](int i) {  // block_1 for local tile i: D1[b][h] = A1[b] rows h*128.. times W1
-      const int b = i % kNA1;
+      const int b = i % kNA1, ba = i % kNA1s;
       const uint32_t ph = (uint32_t)(i / kNA1) & 1u;
-      mbar_wait(&bar_a1_full[b], ph);
+      mbar_wait(&bar_a1_full[ba], (uint32_t)(i / kNA1s) & 1u);
       mbar_wait(&bar_d1_empty[b], ph ^ 1u);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint32_t a_lo = ((a1_addr + (uint32_t)b * kA1Bytes + (uint32_t)h * 128 * 16) >> 4) | lo_a1_c;
+          const uint32_t a_lo = ((a1_addr + (uint32_t)ba * kA1Bytes + (uint32_t)h * 128 * 16) >> 4) | lo_a1_c;
           umma_f16_2w(d1_col + (uint32_t)(b * 2 + h) * 64, a_lo, hi_a1, w1_lo, hi_b, idesc, 0u);
         }
-        umma_commit(&bar_a1_empty[b]);
+        umma_commit(&bar_a1_empty[ba]);
         umma_commit(&bar_d1_full[b]);
       }
       __syncwarp();
@@ -168,48 +188,61 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       const uint32_t sph = (uint32_t)(i / kStages) & 1u, aph = (uint32_t)(i >> 1) & 1u;
       mbar_wait(&bar_slab_full[stage], sph);
       mbar_wait(&bar_d2_empty[acc], aph ^ 1u);
+      // The two issuers take turns: block_2 of tile i+1 is not issued before the last MMA of tile i is in the queue.
+      // Without the turn both warps issue at once whenever their operands are ready, the MMAs of two tiles interleave
+      // (alternating accumulators), both accumulators complete together and the pipe then idles while they drain.
+      if (kTurnTap >= 0) mbar_wait(&bar_turn[par], aph);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a_lo = ((slab_addr + (uint32_t)stage * kStageBytes) >> 4) | lo_a2_c;
+        // One ROLLED loop over the nine taps (4 MMAs per iteration, descriptors advanced by loop-carried adds).  Fully
+        // unrolled, ptxas hoists the preparation of all 37 descriptor pairs to the top of the block, runs out of
+        // uniform registers and spills them (MOV.SPILL / R2UR.FILL): ~10 instructions and several exposed latencies
+        // per MMA, which made the issuing thread - not the tensor pipe - the pace of this stream (tools/mma_seq.cu:
+        // the same 39 MMAs issue in 1873 cycles from a lean loop, 2845 with a few extra instructions per MMA).
+        uint32_t a_t = ((slab_addr + (uint32_t)stage * kStageBytes) >> 4) | lo_a2_c;
+        uint32_t b_t = w2_lo;
         const uint32_t d2 = tmem_base + (uint32_t)acc * 64;
-#pragma unroll
+        int kx = 0;
+#pragma unroll 1
         for (int tap = 0; tap < ((DBG & 128) ? 1 : 9); ++tap) {
-          const int ky = tap / 3, kx = tap % 3;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t aoff = ((uint32_t)(ky * kPW + kx) * 16 + (uint32_t)kk * 2 * kChStride) >> 4;
-            const uint32_t boff = ((uint32_t)tap * 8192 + (uint32_t)kk * 2048) >> 4;
-            umma_f16_2w(d2, a_lo + aoff, hi_a2, w2_lo + boff, hi_b, idesc, (tap | kk) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < 4; ++kk)
+            umma_f16_2w(d2, a_t + (uint32_t)kk * ((2 * kChStride) >> 4), hi_a2, b_t + (uint32_t)kk * (2048u >> 4), hi_b, idesc,
+                        (tap | kk) ? 1u : 0u);
+          if (tap == kTurnTap) mbar_arrive(&bar_turn[par ^ 1]);   // a few MMAs early: covers the other warp's wake-up
+          b_t += 8192u >> 4;
+          if (++kx == 3) { kx = 0; a_t += kPW - 2; } else { a_t += 1; }   // next tap: +1 pixel, or the next halo row
         }
         umma_commit(&bar_slab_empty[stage]);
         // + bias2: D2 += ones[128 x 16] . biasB[64 x 16]
         umma_f16_2w(d2, (smem_u32(ones) >> 4) | ((2048u >> 4) << 16), (128u >> 4) | (1u << 14), w2_lo + ((9u * 8192u) >> 4), hi_b,
                     idesc, 1u);
         umma_commit(&bar_d2_full[acc]);
+        if (kTurnTap >= 9 || (kTurnTap >= 0 && (DBG & 128))) mbar_arrive(&bar_turn[par ^ 1]);
       }
       __syncwarp();
       if (t + 2 * (int)gridDim.x < n_tiles) issue_mma1(i + 2);
     }
   } else if (warp >= 10) {
     // ===================== P: warped patch + im2col operand of block_1 =====================
-    // Two groups of 4 warps, one per tile parity.  A tile's P work is one long dependent chain (coordinates -> four
-    // L2 loads -> interpolation -> patch -> barrier -> im2col rows -> fence), ~2300 cycles when all eight warps work
-    // on the same tile in lock step, which was the slowest stage of the kernel (ncu source page: P never waited for
-    // a free A1 buffer while both MMA issuers spent 39 % of their time waiting for operands).  With the groups
-    // working on alternate tiles each has two tile times per tile and the two samples of a thread overlap their loads.
-    const int grp = (warp - 10) >> 2;
-    const int pt = threadIdx.x - 320 - grp * kPGroup;  // 0..127
+    // kPGroups groups of warps take tiles round robin.  A tile's P work is one long dependent chain (coordinates ->
+    // four L2 loads -> interpolation -> patch -> barrier -> im2col rows -> fence), ~2300 cycles when all eight warps
+    // work on the same tile in lock step, which made P the pace of the kernel (ncu source page: P never waited for a
+    // free A1 buffer while the MMA issuers waited for operands; role knock-outs in SM cycles, tools/front_probe_cycles.sh:
+    // 2230 cycles per tile with P, 1971 without, 1969 for the MMA stream alone).  With g groups each has g tile times
+    // per tile and the samples of a thread overlap their loads.
+    const int grp = (warp - 10) / (8 / kPGroups);
+    const int pt = threadIdx.x - 320 - grp * kPGroup;  // 0..kPGroup-1
     griddep_wait();  // the output buffer may still be read by the previous chunk's kernels; every store follows P's data
     float hm[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     int hm_slot = -1;
-    for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < n_tiles; t += 2 * gridDim.x, i += 2) {
-      const int b = i % kNA1;
-      const uint32_t ph = (uint32_t)(i / kNA1) & 1u;
+    for (int i = grp, t = blockIdx.x + grp * gridDim.x; t < n_tiles; t += kPGroups * gridDim.x, i += kPGroups) {
+      const int b = i % kNA1s;
+      const uint32_t ph = (uint32_t)(i / kNA1s) & 1u;
       const int ls = fast_div(t, p.magic_tpi), rr = t - ls * tiles_per_img;
       const int ty = fast_div(rr, p.magic_tx), tx = rr - ty * p.tiles_x;
       const int slot = p.slot_begin + ls;
-      const int src = p.hinv ? slot / (p.n_h + 1) : slot;
+      const int src = p.hinv ? fast_div(slot, p.magic_nh1) : slot;
       const int j = p.hinv ? slot - src * (p.n_h + 1) : 0;
       const float* img = p.images + (size_t)src * p.H * p.W;
       if (j > 0 && slot != hm_slot) {  // warp-uniform; a CTA's consecutive tiles mostly belong to the same slot
@@ -219,11 +252,11 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         hm_slot = slot;
       }
       // 1. the 12 x 20 patch of the warped image around the tile (zero outside the frame = block_1's padding):
-      //    two samples per thread, their eight loads in flight together; the values are only stored once A1[b] /
-      //    patch_s[b] are free (MMA1 of tile i-3 has consumed them)
-      float pv[2];
+      //    kPSamples samples per thread, their loads in flight together; the values are only stored once A1[b] /
+      //    patch_s[b] are free (MMA1 of tile i - kNA1s has consumed them)
+      float pv[kPSamples];
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kPSamples; ++k) {
         const int s = pt + k * kPGroup;
         const int py = s / kQW, px = s - py * kQW;
         const int y = ty * kTH - 2 + py, x = tx * kTW - 2 + px;
@@ -239,17 +272,22 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         }
         pv[k] = v;
       }
-      mbar_wait(&bar_a1_empty[b], ph ^ 1u);
-      patch_s[b][pt] = to16(pv[0], p.is_bf16);
-      if (pt + kPGroup < kQH * kQW) patch_s[b][pt + kPGroup] = to16(pv[1], p.is_bf16);
-      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      mbar_wait_backoff(&bar_a1_empty[b], ph ^ 1u, kPollNs * 2);
+#pragma unroll
+      for (int k = 0; k < kPSamples; ++k)
+        if (pt + k * kPGroup < kQH * kQW) patch_s[b][pt + k * kPGroup] = to16(pv[k], p.is_bf16);
+      switch (grp) {  // one named barrier per group
+        case 0: asm volatile("bar.sync 1, %0;" ::"n"(kPGroup) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"n"(kPGroup) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"n"(kPGroup) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"n"(kPGroup) : "memory"); break;
+      }
       // 2. A1 row r = halo pixel (hy, hx): its 3x3 neighbourhood (K 0..8), then two constant-one columns that
       //    multiply the (hi, lo) bias rows of W1.  Halo pixels outside the image get an all-zero row, so block_1's
       //    output there is exactly 0 = block_2's zero padding.
       const uint32_t one16 = p.is_bf16 ? 0x3F80u : 0x3C00u;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < kPRows; ++k) {
         const int r = pt + k * kPGroup;
         if (r >= ((DBG & 2) ? 0 : kHalo)) break;
         const int hy = r / kPW, hx = r - hy * kPW;
@@ -269,7 +307,8 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         *reinterpret_cast<uint4*>(dst + kA1Rows * 16) = c1;     // tap 8, one, one, zero padding
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&bar_a1_full[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a1_full[b]);   // one arrival per warp (see the note on shared-memory traffic above)
     }
   } else if (warp >= 6) {
     // ===================== E1: block_1 epilogue -> block_2's input slab =====================
@@ -278,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
       const int b = i % kNA1, stage = i % kStages;
       const uint32_t ph = (uint32_t)(i / kNA1) & 1u, sph = (uint32_t)(i / kStages) & 1u;
-      mbar_wait(&bar_d1_full[b], ph);
+      mbar_wait_backoff(&bar_d1_full[b], ph, kPollNs);
       mbar_wait(&bar_slab_empty[stage], sph ^ 1u);
       tc_fence_after();
       uint8_t* slab = slab0 + (size_t)stage * kStageBytes;
@@ -307,9 +346,12 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         }
       }
       tc_fence_before();
-      mbar_arrive(&bar_d1_empty[b]);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(&bar_slab_full[stage]);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bar_d1_empty[b]);
+        mbar_arrive(&bar_slab_full[stage]);
+      }
     }
   } else {
     // ===================== E2: block_2 epilogue (bias, ReLU, 2x2 max-pool, C8 store) =====================
@@ -323,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       const int ls = fast_div(t, p.magic_tpi), rr = t - ls * tiles_per_img;
       const int ty = fast_div(rr, p.magic_tx), tx = rr - ty * p.tiles_x;
       const int y = ty * kTH + g, x = tx * kTW + r;
-      mbar_wait(&bar_d2_full[acc], aph);
+      mbar_wait_backoff(&bar_d2_full[acc], aph, kPollNs);
       tc_fence_after();
       uint32_t v[64];
       const uint32_t taddr = tmem_base + (uint32_t)acc * 64 + ((uint32_t)(q * 32) << 16);
@@ -333,7 +375,8 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         tmem_ld_wait();
       }
       tc_fence_before();
-      mbar_arrive(&bar_d2_empty[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_d2_empty[acc]);
       if (DBG & 32) continue;
       uint32_t h2[32];
 #pragma unroll
@@ -373,17 +416,20 @@ int spn_front_tc_launch(spn_ctx* ctx, const float* d_images, const float* d_hinv
   memset(&p, 0, sizeof(p));
   p.images = d_images; p.hinv = d_hinv; p.n_h = n_h; p.slot_begin = slot_begin; p.n_slots = n_slots;
   p.H = H; p.W = W; p.tiles_x = spn_cdiv(W, kTW); p.tiles_y = spn_cdiv(H, kTH); p.is_bf16 = bf;
-  p.magic_tpi = fast_div_magic(p.tiles_x * p.tiles_y); p.magic_tx = fast_div_magic(p.tiles_x);
+  p.magic_tpi = fast_div_magic(p.tiles_x * p.tiles_y); p.magic_tx = fast_div_magic(p.tiles_x); p.magic_nh1 = fast_div_magic(n_h + 1);
   SPN_REQUIRE((long long)n_slots * p.tiles_x * p.tiles_y * (p.tiles_x * p.tiles_y) < (1ll << 40), "too many tiles for one launch");
+  SPN_REQUIRE((long long)(slot_begin + n_slots) * (n_h + 1) < (1ll << 40) && (long long)H * W < (1ll << 31), "slot range / image too large");
   p.w1img = w1img; p.w2img = L2.w16[bf];
   p.out = d_out;
-  const size_t dyn = (size_t)kW2Bytes + kW1Bytes + kNA1 * kA1Bytes + kOnesBytes + (size_t)kStages * kStageBytes + 1024;
+  const size_t dyn = (size_t)kW2Bytes + kW1Bytes + kNA1s * kA1Bytes + kOnesBytes + (size_t)kStages * kStageBytes + 1024;
   const long long tiles = (long long)n_slots * p.tiles_x * p.tiles_y;
   const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
   void (*kern)(const FrontParams) = front_tc_kernel<0>;
 #ifdef SPN_FRONT_DBG_BUILD  // diagnostic build only (tools/front_probe.py): role knock-out instantiations, wrong results
   switch (ctx->opt_front_variant) {
     case 0: break;
+    case 1: kern = front_tc_kernel<1>; break;
+    case 2: kern = front_tc_kernel<2>; break;
     case 3: kern = front_tc_kernel<3>; break;
     case 12: kern = front_tc_kernel<12>; break;
     case 16: kern = front_tc_kernel<16>; break;

@@ -71,8 +71,10 @@ __device__ __forceinline__ float bilinear_zero_nb(const float* __restrict__ img,
   const float mx0 = (x0 >= 0 && ok) ? wx0 : 0.f, mx1 = (x0 + 1 < W && ok) ? wx1 : 0.f;
   const float my0 = (y0 >= 0) ? wy0 : 0.f, my1 = (y0 + 1 < H) ? wy1 : 0.f;
   const int xa = max(x0, 0), xb = min(x0 + 1, W - 1), ya = max(y0, 0), yb = min(y0 + 1, H - 1);
-  const float v00 = __ldg(&img[(size_t)ya * W + xa]), v01 = __ldg(&img[(size_t)ya * W + xb]);
-  const float v10 = __ldg(&img[(size_t)yb * W + xa]), v11 = __ldg(&img[(size_t)yb * W + xb]);
+  // 32-bit element offsets (H * W < 2^31 is checked by every caller's shape limits): one 64-bit base + four offsets
+  const unsigned ra = (unsigned)(ya * W), rb = (unsigned)(yb * W);
+  const float v00 = __ldg(img + (ra + (unsigned)xa)), v01 = __ldg(img + (ra + (unsigned)xb));
+  const float v10 = __ldg(img + (rb + (unsigned)xa)), v11 = __ldg(img + (rb + (unsigned)xb));
   float v = v00 * (mx0 * my0);
   v = fmaf(v01, mx1 * my0, v);
   v = fmaf(v10, mx0 * my1, v);

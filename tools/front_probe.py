@@ -12,10 +12,13 @@ imgs = torch.rand((1, H, W), device=dev)
 h, hinv = ctx.sample_homographies(bench.HA_CFG["params"], 1, 0, NH, H, W)
 hinv = hinv.view(1, NH, 3, 3)
 # needs a library built with SPN_FRONT_DBG_BUILD=1 (extra template instantiations)
-names = {0: "baseline", 3: "P: nothing", 12: "E1: nothing", 16: "E2: no stores", 32: "E2: no ALU/stores", 96: "E2: nothing",
+names = {0: "baseline", 1: "P: no sampling", 2: "P: no A1 rows", 3: "P: nothing", 12: "E1: nothing", 16: "E2: no stores", 32: "E2: no ALU/stores", 96: "E2: nothing",
          128: "M: 4 of 36 MMA2", 111: "only MMAs", 15: "P+E1 off", 108: "E1+E2 off", 99: "P+E2 off", 0.5: "baseline again"}
+if os.environ.get("SPN_PROBE_BASELINE_ONLY"):
+    names = {0: "baseline"}
 for dbg, name in names.items():
-    ctx.set_option("front_variant", int(dbg))
+    if int(dbg) != 0 or not os.environ.get("SPN_PROBE_BASELINE_ONLY"):
+        ctx.set_option("front_variant", int(dbg))
     for _ in range(2):
         ctx.encoder_forward_ha(imgs, hinv, 0, NH + 1, 1)
     torch.cuda.synchronize()
