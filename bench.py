@@ -408,7 +408,7 @@ def main():
     ap.add_argument("--images-per-step", type=int, default=128,
                     help="images per GPU per step; 128 makes a step ~170 ms so the timed region of the default run is > 3 s "
                          "(the sustained, power-capped regime rather than a burst)")
-    ap.add_argument("--max-forwards", type=int, default=100)
+    ap.add_argument("--max-forwards", type=int, default=400)
     ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--ref-homographies", type=int, default=25, help="homographies in the bounded CPU sample (of 100)")
     ap.add_argument("--steps-ref", type=int, default=1)

@@ -22,7 +22,7 @@ whose result export.py:69 discards is not computed.
 
 Extension keys under ``homography_adaptation`` (optional): ``sampler`` 'device' (default, spn_sample_homographies)
 or 'numpy' (the reference's host sampler and RNG order), ``seed``, ``images_per_launch`` (default 1),
-``max_forwards`` (forwards per encoder launch, default 128), ``streams`` (concurrent CUDA streams, default 1).
+``max_forwards`` (forwards per encoder launch, default 400), ``streams`` (concurrent CUDA streams, default 1).
 
 Geometry: homographies that come from the host (the numpy sampler, or matrices passed in) go through
 ``utils.kornia_geometry.sampling_matrices`` - the reference's own torch calls - and the kernels then follow kornia's
@@ -59,7 +59,7 @@ class HomographyAdaptation:
         self.model = model.eval()
         self.device = device
         self.sampler = Homographic_aug(self.ha, device)
-        self.max_forwards = int(self.ha.get("max_forwards", 128))
+        self.max_forwards = int(self.ha.get("max_forwards", 400))
         self.seed = int(self.ha.get("seed", 0))
         self.n_streams = max(1, int(self.ha.get("streams", 1)))
         self.index_stride = max(1, int(self.ha.get("index_stride", 1)))   # rank sharding: image k of a group has index first + k*stride
