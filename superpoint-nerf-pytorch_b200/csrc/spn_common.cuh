@@ -61,6 +61,7 @@ struct spn_ctx {
   void* tc = nullptr;       // tcgen05 path state (conv_tc.cu)
   // options (spn_set_option): A/B switches of the tensor-core path, all on by default
   int opt_fold = 1;         // 3x3 layers: horizontal taps folded into N (conv_fold.cu) instead of nine descriptors
+  int opt_fold_hybrid = 0;  // A/B: 64-channel-input folded layers with kx = 2 as a separate shifted N = 64 MMA (conv_fold.cu, HYB; measured 15 % slower)
   int opt_fuse_front = 1;   // warp + block_1 + block_2 in one kernel (front_tc.cu)
   int opt_fuse_head = 1;    // convPb + softmax + depth-to-space in one kernel (head_tc.cu)
   int opt_pdl = 1;          // programmatic dependent launch along the tensor-core chain

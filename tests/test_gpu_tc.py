@@ -226,6 +226,29 @@ def test_unfolded_conv_kernel_still_correct(sp_model, monkeypatch, name, shape):
     assert rel_err(a, b) < 2e-3      # same operands, different summation order + one fp16 rounding
 
 
+@pytest.mark.parametrize("name,shape", [("backbone.block_3", (2, 64, 48, 40)), ("backbone.block_4", (1, 64, 40, 72)),
+                                        ("backbone.block_5", (1, 64, 30, 44))])
+def test_hybrid_fold_option(sp_model, name, shape):
+    """Option fold_hybrid (conv_fold_kernel<true>: kx = 0, 1 folded into one N = 128 MMA, kx = 2 as a shifted N = 64 MMA
+    accumulating into the same columns) is an A/B variant for the 64-channel-input layers (measured slower, off by
+    default): it must stay correct."""
+    m, sd = sp_model
+    ctx = m.native()
+    lid = LAYER_ID[name]
+    _n, cin, cout, k, relu, pool = O.layer_table(superpoint=True)[lid]
+    rng = np.random.RandomState(lid + 300)
+    x = torch.from_numpy(np.maximum(rng.randn(*shape), 0).astype(np.float32))
+    want = O.vgg_block(sd, name, x.half().float(), k, relu, pool).numpy()
+    b = ctx.conv_layer(lid, x.cuda(), 1, relu=relu, pool=pool, cout=cout).cpu().numpy()
+    ctx.set_option("fold_hybrid", 1)
+    try:
+        a = ctx.conv_layer(lid, x.cuda(), 1, relu=relu, pool=pool, cout=cout).cpu().numpy()
+    finally:
+        ctx.set_option("fold_hybrid", 0)
+    assert rel_err(a, want) < FAST and rel_err(b, want) < FAST
+    assert rel_err(a, b) < 2e-3      # same operands, the kx = 2 term is summed inside the accumulator instead of after it
+
+
 def test_fast_path_is_deterministic_across_chunkings():
     """The tensor-core kernels are chained with programmatic dependent launch and reuse two activation buffers from
     chunk to chunk: the result must not depend on how the homography slots are chunked, nor vary from run to run
