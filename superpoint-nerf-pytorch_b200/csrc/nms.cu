@@ -10,8 +10,7 @@
 //     a candidate is SUPPRESSED iff some footprint neighbour is KEPT,
 // with rank = (score desc, row-major index asc).  The kernel iterates that rule to the fixed point with one
 // __syncthreads per round; each round only touches still-undecided pixels.
-// One 1024-thread CTA owns one image, so a batch of B images runs B CTAs concurrently (the export path batches
-// >= 148 images); status bytes live in a caller-invisible scratch buffer and stay L1/L2 resident.
+// Status bytes live in a caller-invisible scratch buffer and stay L1/L2 resident.
 #include <math.h>
 
 #include <cooperative_groups.h>
@@ -322,125 +321,57 @@ nms_rounds_bits_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__
   }
 }
 
-// Phase 2 (one CTA per image): optional top-k, scattered / thresholded maps, row-major keypoint list.
+// Phase 2: ordered compaction over S CTAs per image + (optional) top-k selection on the compacted survivor list.
+//
+// nms_emit_kernel<MODE>: every CTA owns a contiguous pixel range of one image (row-major), counts the pixels that pass
+// the predicate, publishes the count and looks back over the earlier segments of the same image (decoupled look-back:
+// a CTA's segment index is an atomic ticket, so everything it waits for has already started and publishes before it
+// waits itself), then writes its elements at their global row-major rank.
+//   MODE 0: predicate = survived the NMS; output = (ordered key, pixel index) list for the top-k selection
+//   MODE 1: predicate = survived and >= det_thresh; output = keypoint list (row, col), optional dense maps, count
+// One CTA per image (the round-1 layout) made this phase 63 us for ONE 240x320 image - two latency-bound passes of 75
+// iterations per warp on a single SM; with S = 2 x SMs / B segments a single image takes a few microseconds per pass.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kThreads)
-nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ status_all, int H, int W, int top_k,
-                    float det_thresh, float* __restrict__ nms_all, int32_t* __restrict__ pred_all,
-                    int32_t* __restrict__ kp_all, int32_t* __restrict__ kp_count, int max_kp,
-                    uint32_t* __restrict__ list_all) {
+nms_emit_kernel(const float* __restrict__ prob_all, const uint8_t* __restrict__ status_all, int H, int W, int S,
+                float det_thresh, float* __restrict__ nms_all, int32_t* __restrict__ pred_all,
+                int32_t* __restrict__ kp_all, int32_t* __restrict__ kp_count, int max_kp,
+                uint32_t* __restrict__ list_all, int* __restrict__ list_count, unsigned* __restrict__ flags,
+                unsigned* __restrict__ ticket) {
   __shared__ int s_warp[kThreads / 32];
-  __shared__ unsigned s_hist[256];
-  __shared__ unsigned s_sel[2];
-  const int b = blockIdx.x;
+  __shared__ unsigned s_ticket;
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int b = (int)(s_ticket / (unsigned)S), sg = (int)(s_ticket % (unsigned)S);
   const int P = H * W;
   const float* prob = prob_all + (size_t)b * P;
-  uint8_t* status = status_all + (size_t)b * P;
-  const int tid = threadIdx.x;
+  const uint8_t* status = status_all + (size_t)b * P;
+  const int seg_px = (((P + S - 1) / S) + 31) & ~31;                  // CTA range, multiple of 32
+  const int c_begin = min(P, sg * seg_px), c_end = min(P, c_begin + seg_px);
+  const int wseg = ((c_end - c_begin + kThreads - 1) / kThreads) * 32;  // warp range, multiple of 32
+  const int p_begin = min(c_end, c_begin + warp * wseg), p_end = min(c_end, p_begin + wseg);
 
-  // ---- optional top-k over the survivors: (score desc, index asc) ----
-  // The survivors (a few percent of the pixels) are first compacted, in index order, into a (key, index) list; the
-  // radix select and the tie ranking then walk that list instead of the whole image.
-  if (top_k > 0) {
-    const int lane = tid & 31, warp = tid >> 5;
-    const int seg = ((P + kThreads - 1) / kThreads) * 32;  // warp w owns pixels [w*seg, (w+1)*seg)
-    const int pb = warp * seg, pe = min(P, pb + seg);
-    int mine = 0;
-    for (int p = pb + lane; p < pe; p += 32) mine += (status[p] == 2);
-    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    if (lane == 0) s_warp[warp] = mine;
-    __syncthreads();
-    int kept = 0, base = 0;
-    for (int w = 0; w < kThreads / 32; ++w) {
-      if (w < warp) base += s_warp[w];
-      kept += s_warp[w];
-    }
-    __syncthreads();
-    if (kept > top_k) {
-      uint32_t* lkey = list_all + (size_t)b * 2 * P;   // [kept] ordered keys
-      int32_t* lidx = reinterpret_cast<int32_t*>(lkey + P);  // [kept] pixel indices, ascending
-      for (int p0 = pb; p0 < pe; p0 += 32) {
-        const int p = p0 + lane;
-        const bool k2 = p < pe && status[p] == 2;
-        const unsigned bal = __ballot_sync(0xffffffffu, k2);
-        if (k2) {
-          const int pos = base + __popc(bal & ((1u << lane) - 1u));
-          lkey[pos] = ordered_key(__ldg(&prob[p]));
-          lidx[pos] = p;
-        }
-        base += __popc(bal);
-      }
-      __syncthreads();  // list complete (block-scope visibility of the global writes)
-      uint32_t prefix = 0, maskbits = 0;
-      unsigned want = (unsigned)top_k;  // rank (1-based, descending) of the threshold element
-      for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        if (tid < 256) s_hist[tid] = 0;
-        __syncthreads();
-        for (int i = tid; i < kept; i += kThreads) {
-          const uint32_t key = lkey[i];
-          if ((key & maskbits) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-          unsigned cum = 0;
-          int bin = 255;
-          for (; bin > 0; --bin) {
-            if (cum + s_hist[bin] >= want) break;
-            cum += s_hist[bin];
-          }
-          s_sel[0] = (unsigned)bin;
-          s_sel[1] = want - cum;
-        }
-        __syncthreads();
-        prefix |= s_sel[0] << shift;
-        maskbits |= 0xffu << shift;
-        want = s_sel[1];
-        __syncthreads();
-      }
-      // prefix = key of the top_k-th survivor; keep keys > prefix and the first `want` equal keys in index order.
-      // Warp w owns list positions [w*lseg, (w+1)*lseg): count its ties, one block scan, then rank them in order.
-      const int lseg = ((kept + kThreads - 1) / kThreads) * 32;
-      const int lb = min(kept, warp * lseg), le = min(kept, lb + lseg);
-      int tcnt = 0;
-      for (int i = lb + lane; i < le; i += 32) {
-        const uint32_t key = lkey[i];
-        if (key < prefix) status[lidx[i]] = 0;
-        tcnt += (key == prefix);
-      }
-      for (int o = 16; o > 0; o >>= 1) tcnt += __shfl_xor_sync(0xffffffffu, tcnt, o);
-      if (lane == 0) s_warp[warp] = tcnt;
-      __syncthreads();
-      int tie_base = 0;
-      for (int w = 0; w < warp; ++w) tie_base += s_warp[w];
-      if (tcnt > 0) {  // warp-uniform
-        for (int i0 = lb; i0 < le; i0 += 32) {
-          const int i = i0 + lane;
-          const bool tie = i < le && lkey[i] == prefix;
-          const unsigned bal = __ballot_sync(0xffffffffu, tie);
-          if (tie && (unsigned)(tie_base + __popc(bal & ((1u << lane) - 1u))) >= want) status[lidx[i]] = 0;
-          tie_base += __popc(bal);
-        }
-      }
-      __syncthreads();
-    }
-  }
-
-  // ---- outputs: scattered map, thresholded map, row-major keypoint list ----
-  // Warp w owns the contiguous pixel range [w*seg, (w+1)*seg): pass 1 counts its keypoints (no barriers, loads in
-  // flight back to back), one block scan orders the 32 warps, pass 2 writes maps and keypoints in row-major order.
-  float* nms = nms_all ? nms_all + (size_t)b * P : nullptr;
-  int32_t* pred = pred_all ? pred_all + (size_t)b * P : nullptr;
-  int32_t* kp = kp_all ? kp_all + (size_t)b * max_kp * 2 : nullptr;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int seg = ((P + kThreads - 1) / kThreads) * 32;  // multiple of 32
-  const int p_begin = warp * seg, p_end = min(P, p_begin + seg);
+  auto pass = [&](int p, float& v) -> bool {   // predicate + the value the outputs need
+    v = (status[p] == 2) ? __ldg(&prob[p]) : 0.0f;
+    return MODE == 0 ? status[p] == 2 : v >= det_thresh;
+  };
   int cnt = 0;
   for (int p = p_begin + lane; p < p_end; p += 32) {
-    const float v = (status[p] == 2) ? __ldg(&prob[p]) : 0.0f;
-    cnt += (v >= det_thresh);
+    float v;
+    cnt += pass(p, v) ? 1 : 0;
   }
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  __syncthreads();
   if (lane == 0) s_warp[warp] = cnt;
   __syncthreads();
   int base = 0, total = 0;
@@ -449,25 +380,120 @@ nms_finalize_kernel(const float* __restrict__ prob_all, uint8_t* __restrict__ st
     if (w < warp) base += c;
     total += c;
   }
+  if (tid == 0) {
+    st_release_u32(&flags[b * S + sg], ((unsigned)total << 1) | 1u);
+    int before = 0;
+    for (int k = sg - 1; k >= 0; --k) {
+      unsigned f;
+      do { f = ld_acquire_u32(&flags[b * S + k]); } while (!(f & 1u));
+      before += (int)(f >> 1);
+    }
+    s_base = before;
+    if (sg == S - 1) {
+      if (MODE == 0) list_count[b] = before + total;
+      else if (kp_count) kp_count[b] = before + total;
+    }
+  }
+  __syncthreads();
+  base += s_base;
+
+  float* nms = (MODE == 1 && nms_all) ? nms_all + (size_t)b * P : nullptr;
+  int32_t* pred = (MODE == 1 && pred_all) ? pred_all + (size_t)b * P : nullptr;
+  int32_t* kp = (MODE == 1 && kp_all) ? kp_all + (size_t)b * max_kp * 2 : nullptr;
+  uint32_t* lkey = MODE == 0 ? list_all + (size_t)b * 2 * P : nullptr;   // [kept] ordered keys
+  int32_t* lidx = MODE == 0 ? reinterpret_cast<int32_t*>(lkey + P) : nullptr;  // [kept] pixel indices, ascending
   for (int p0 = p_begin; p0 < p_end; p0 += 32) {
     const int p = p0 + lane;
-    bool is_kp = false;
+    bool hit = false;
+    float v = 0.f;
     if (p < p_end) {
-      const float v = (status[p] == 2) ? __ldg(&prob[p]) : 0.0f;
-      is_kp = v >= det_thresh;
+      hit = pass(p, v);
       if (nms) nms[p] = v;
-      if (pred) pred[p] = is_kp ? 1 : 0;
+      if (pred) pred[p] = hit ? 1 : 0;
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, is_kp);
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
     const int rank = base + __popc(bal & ((1u << lane) - 1u));
-    if (is_kp && kp && rank < max_kp) {
-      const int y = p / W;
-      kp[2 * rank] = y;
-      kp[2 * rank + 1] = p - y * W;
+    if (hit) {
+      if (MODE == 0) {
+        lkey[rank] = ordered_key(v);
+        lidx[rank] = p;
+      } else if (kp && rank < max_kp) {
+        const int y = p / W;
+        kp[2 * rank] = y;
+        kp[2 * rank + 1] = p - y * W;
+      }
     }
     base += __popc(bal);
   }
-  if (kp_count && tid == 0) kp_count[b] = total;
+}
+
+// top-k over the survivors: (score desc, index asc).  One CTA per image walks the compacted (key, index) list written
+// by nms_emit_kernel<0> (a few percent of the pixels): 4-pass radix select of the top_k-th key, then the ties are ranked
+// in index order; the losers' status bytes are cleared so that nms_emit_kernel<1> drops them.
+__global__ void __launch_bounds__(kThreads)
+nms_topk_select_kernel(uint8_t* __restrict__ status_all, int P, int top_k, const uint32_t* __restrict__ list_all,
+                       const int* __restrict__ list_count) {
+  __shared__ int s_warp[kThreads / 32];
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned s_sel[2];
+  const int b = blockIdx.x;
+  const int kept = list_count[b];
+  if (kept <= top_k) return;
+  uint8_t* status = status_all + (size_t)b * P;
+  const uint32_t* lkey = list_all + (size_t)b * 2 * P;
+  const int32_t* lidx = reinterpret_cast<const int32_t*>(lkey + P);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t prefix = 0, maskbits = 0;
+  unsigned want = (unsigned)top_k;  // rank (1-based, descending) of the threshold element
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < kept; i += kThreads) {
+      const uint32_t key = lkey[i];
+      if ((key & maskbits) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned cum = 0;
+      int bin = 255;
+      for (; bin > 0; --bin) {
+        if (cum + s_hist[bin] >= want) break;
+        cum += s_hist[bin];
+      }
+      s_sel[0] = (unsigned)bin;
+      s_sel[1] = want - cum;
+    }
+    __syncthreads();
+    prefix |= s_sel[0] << shift;
+    maskbits |= 0xffu << shift;
+    want = s_sel[1];
+    __syncthreads();
+  }
+  // prefix = key of the top_k-th survivor; keep keys > prefix and the first `want` equal keys in index order.
+  // Warp w owns list positions [w*lseg, (w+1)*lseg): count its ties, one block scan, then rank them in order.
+  const int lseg = ((kept + kThreads - 1) / kThreads) * 32;
+  const int lb = min(kept, warp * lseg), le = min(kept, lb + lseg);
+  int tcnt = 0;
+  for (int i = lb + lane; i < le; i += 32) {
+    const uint32_t key = lkey[i];
+    if (key < prefix) status[lidx[i]] = 0;
+    tcnt += (key == prefix);
+  }
+  for (int o = 16; o > 0; o >>= 1) tcnt += __shfl_xor_sync(0xffffffffu, tcnt, o);
+  if (lane == 0) s_warp[warp] = tcnt;
+  __syncthreads();
+  int tie_base = 0;
+  for (int w = 0; w < warp; ++w) tie_base += s_warp[w];
+  if (tcnt > 0) {  // warp-uniform
+    for (int i0 = lb; i0 < le; i0 += 32) {
+      const int i = i0 + lane;
+      const bool tie = i < le && lkey[i] == prefix;
+      const unsigned bal = __ballot_sync(0xffffffffu, tie);
+      if (tie && (unsigned)(tie_base + __popc(bal & ((1u << lane) - 1u))) >= want) status[lidx[i]] = 0;
+      tie_base += __popc(bal);
+    }
+  }
 }
 
 }  // namespace
@@ -511,7 +537,11 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
   SPN_REQUIRE(n_tiles < (1ll << 28), "spn_box_nms_topk: batch too large");
   const size_t lists_bytes = (2 * (size_t)n_tiles * sizeof(int) + 255) & ~(size_t)255;
   const size_t topk_bytes = top_k > 0 ? (size_t)B * H * W * 8 : 0;   // (key, index) list of the survivors, per image
-  int rc = spn_ensure_aux(ctx, status_bytes + 256 + lists_bytes + topk_bytes, s);
+  // phase 2 geometry: S segments (CTAs) per image, about two CTAs per SM in total, at least 2048 pixels each
+  int S = (2 * ctx->sm_count + B - 1) / B;
+  S = max(1, min(S, min(32, H * W / 2048)));
+  const size_t sync_bytes = ((size_t)(2 * B * S + B + 8) * sizeof(unsigned) + 255) & ~(size_t)255;  // flags x2, list counts, tickets
+  int rc = spn_ensure_aux(ctx, status_bytes + 256 + lists_bytes + topk_bytes + sync_bytes, s);
   if (rc) return rc;
   uint8_t* status = (uint8_t*)ctx->aux;
   unsigned* pend = (unsigned*)(ctx->aux + status_bytes);
@@ -545,8 +575,19 @@ extern "C" int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H,
     SPN_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kThreads), args, smem, s));
   }
   ctx->launches++;
-  nms_finalize_kernel<<<B, kThreads, 0, s>>>(d_prob, status, H, W, top_k, det_thresh, d_nms, d_pred, d_kp, d_kp_count, max_kp,
-                                             topk_list);
+  unsigned* sync = (unsigned*)(ctx->aux + status_bytes + 256 + lists_bytes + topk_bytes);
+  unsigned* flags0 = sync, *flags1 = sync + (size_t)B * S, *tickets = sync + 2 * (size_t)B * S;
+  int* list_count = (int*)(tickets + 8);
+  SPN_CUDA(cudaMemsetAsync(sync, 0, sync_bytes, s));
+  if (top_k > 0) {
+    nms_emit_kernel<0><<<B * S, kThreads, 0, s>>>(d_prob, status, H, W, S, det_thresh, nullptr, nullptr, nullptr, nullptr, 0,
+                                                  topk_list, list_count, flags0, tickets);
+    SPN_CHECK_LAUNCH(ctx);
+    nms_topk_select_kernel<<<B, kThreads, 0, s>>>(status, H * W, top_k, topk_list, list_count);
+    SPN_CHECK_LAUNCH(ctx);
+  }
+  nms_emit_kernel<1><<<B * S, kThreads, 0, s>>>(d_prob, status, H, W, S, det_thresh, d_nms, d_pred, d_kp, d_kp_count, max_kp,
+                                                nullptr, nullptr, flags1, tickets + 1);
   SPN_CHECK_LAUNCH(ctx);
   return SPN_OK;
 }
