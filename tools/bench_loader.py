@@ -32,6 +32,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--images-per-launch", type=int, default=64)
+    ap.add_argument("--max-forwards", type=int, default=400)
     args = ap.parse_args()
     tmp = Path(tempfile.mkdtemp(prefix="spn_loader_"))
     try:
@@ -49,7 +51,8 @@ def main():
             data["loader_workers"] = args.workers
         mcfg = dict(copy.deepcopy(bench.MODEL_CFG), precision="f16")
         cfg = {"data": data, "model": mcfg,
-               "homography_adaptation": dict(copy.deepcopy(bench.HA_CFG), sampler="device", seed=1, images_per_launch=32, max_forwards=100)}
+               "homography_adaptation": dict(copy.deepcopy(bench.HA_CFG), sampler="device", seed=1, images_per_launch=args.images_per_launch,
+                                            max_forwards=args.max_forwards)}
         loader = get_loader(cfg, "export_pseudo_labels", device="cuda", export_split="training")
         for _ in zip(range(32), loader):
             pass
@@ -62,7 +65,8 @@ def main():
         model.load_state_dict(bench.random_init_state_dict())
         warm = copy.deepcopy(cfg)
         warm["data"]["experiment_name"] = "warm"
-        ExportDetections(warm, model, list(zip(range(64), loader)) and [b for _, b in zip(range(64), loader)], "training", True, "cuda")
+        n_warm = max(64, 2 * args.images_per_launch)   # two full groups: workspace, pinned staging and allocator pools at their final size
+        ExportDetections(warm, model, [b for _, b in zip(range(n_warm), loader)], "training", True, "cuda")
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ExportDetections(cfg, model, loader, "training", True, "cuda")
@@ -70,7 +74,8 @@ def main():
         t_exp = time.perf_counter() - t0
         files = len(list(Path(tmp, "exper", "outputs", "loader_bench", "training").glob("*.npy")))
         print(json.dumps({"images": n, "loader_only_img_per_s": n / t_load, "export_with_loader_img_per_s": files / t_exp,
-                          "files_written": files, "workers": loader.workers, "jpeg": "640x480 q90 -> 240x320",
+                          "files_written": files, "workers": loader.workers, "images_per_launch": args.images_per_launch,
+                          "max_forwards": args.max_forwards, "jpeg": "640x480 q90 -> 240x320",
                           "note": "export = decode (host threads) + resize kernel + HA x100 (f16) + NMS + .npy per image"}))
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
