@@ -92,6 +92,25 @@ def test_box_nms_batched_and_empty(ctx):
     assert int(r["kp_count"][2]) == 0
 
 
+@pytest.mark.parametrize("top_k", [0, 150])
+def test_box_nms_batched_multi_segment(ctx, top_k):
+    """Several images, each split over several CTAs in phase 2 (nms_emit_kernel's look-back across segments): row-major
+    keypoint order, counts and maps per image, with an empty image and one whose keypoints all sit in the last rows."""
+    rng = np.random.RandomState(5)
+    B, h, w = 4, 120, 160
+    p = (rng.rand(B, h, w) ** 6).astype(np.float32)
+    p[1] = 0.0
+    p[2, : h - 9] = 0.0
+    r = ctx.box_nms(torch.from_numpy(p).cuda(), 4, 0.1, 0.05, top_k, det_thresh=0.05, want_map=True, want_pred=True, max_kp=h * w)
+    for i in range(B):
+        want = O.box_nms_c(p[i], 4, 0.1, 0.05, top_k).numpy()
+        assert np.array_equal(r["nms"][i].cpu().numpy(), want), i
+        kp_want = np.argwhere(want >= 0.05)
+        n = int(r["kp_count"][i])
+        assert n == len(kp_want) and np.array_equal(r["kp"][i, :n].cpu().numpy(), kp_want), i
+        assert np.array_equal(r["pred"][i].cpu().numpy(), (want >= 0.05).astype(np.int32))
+
+
 # ------------------------------------------------------------------------------------------------ forward
 @pytest.mark.parametrize("tag,cfg", [("magicpoint", MP_MODEL), ("superpoint", SP_MODEL)])
 def test_forward_strict_vs_golden(P, golden, tag, cfg):
@@ -503,7 +522,7 @@ def test_dense_descriptors_vs_torch(ctx, shape, grid):
 
 def test_box_nms_topk_with_many_ties(ctx):
     """top-k where the k-th score is shared by many pixels spread over the whole image: the tie break (lower row-major
-    index first) runs through the warp-segment ranking of nms_finalize_kernel."""
+    index first) runs through the warp-segment ranking of nms_topk_select_kernel."""
     rng = np.random.RandomState(11)
     for (h, w, k) in [(240, 320, 300), (480, 640, 1000), (37, 53, 40)]:
         p = (np.round(rng.rand(h, w) * 3) / 3 * 0.5 + 0.25).astype(np.float32)   # four distinct values
