@@ -66,7 +66,8 @@ SPN_API int spn_destroy(spn_ctx* ctx);
  * with the horizontal taps folded into N = 192), "fuse_front" (warp + block_1 + block_2 in one kernel), "fuse_head"
  * (convPb + softmax + depth-to-space in one kernel), "pdl" (programmatic dependent launch): all default to 1.
  * Kept for A/B, default 0 (both measured slower): "front_pair" (the fused front end as a 2-CTA cluster with
- * cta_group::2 MMAs), "fold_hybrid" (64-channel-input folded layers with kx = 2 as a separate shifted N = 64 MMA). */
+ * cta_group::2 MMAs), "fold_hybrid" (64-channel-input folded layers with kx = 2 as a separate shifted N = 64 MMA).
+ * "ws_guard" (default 0): see spn_check_guards. */
 SPN_API int spn_set_option(spn_ctx* ctx, const char* name, int value);
 
 /* BN fold + pack + upload of one VGG_Block (conv2d + BatchNorm2d eval, eps as given).
@@ -142,6 +143,13 @@ SPN_API int spn_box_nms_topk(spn_ctx* ctx, const float* d_prob, int B, int H, in
 /* Statistics of the last spn_box_nms_topk call with the same (B,H,W): h_out[0] = global rounds (grid-wide
  * synchronisations), h_out[1] = tile-local iterations, h_out[2] = tile visits.  Synchronises the device. */
 SPN_API int spn_nms_stats(spn_ctx* ctx, int B, int H, int W, int64_t* h_out);
+
+/* Memory-safety probe (no reference counterpart; compute-sanitizer is not available on the target pool).  The
+ * context's workspace and scratch buffer are allocated with a 64 KB band of 0xA5 before and after the usable range,
+ * and the tensor-core workspace plan leaves 4 KB gaps between its regions which option "ws_guard" = 1 paints before
+ * every encoder pass.  *h_bad = number of guard bytes that no longer hold the pattern (0 = no kernel wrote outside
+ * its region).  Synchronises the device. */
+SPN_API int spn_check_guards(spn_ctx* ctx, int64_t* h_bad);
 
 /* ExportDetections.step warp part (export.py:51-66): for every image i < n_images and homography j < n_h
  *   slot = i*(n_h+1) + 1 + j : d_warped[slot] = warp_perspective(image_i, H_ij, bilinear, align_corners=True)

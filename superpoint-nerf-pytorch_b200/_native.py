@@ -52,6 +52,7 @@ PROTOTYPES = {
     "spn_detect_describe": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "spn_box_nms_topk": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _i, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     "spn_nms_stats": (_i, [_vp, _i, _i, _i, _vp]),
+    "spn_check_guards": (_i, [_vp, _vp]),
     "spn_warp_batch": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "spn_ha_aggregate": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "spn_sample_homographies": (_i, [_vp, C.POINTER(HomographyParams), C.c_uint64, C.c_uint64, _i, _i, _i, _vp, _vp, _vp]),
@@ -301,6 +302,13 @@ class Context:
                    int(top_k), C.c_float(det), _ptr(out["nms"]), _ptr(out["pred"]), _ptr(out["kp"]), _ptr(out["kp_count"]),
                    int(max_kp), self._s())
         return out
+
+    def check_guards(self):
+        """Number of guard bytes (bands around the workspace / scratch buffer, gaps between the carved regions when
+        option ``ws_guard`` is on) that a kernel overwrote; 0 = none.  Synchronises the device."""
+        out = (C.c_int64 * 1)()
+        self._call("spn_check_guards", self.handle, C.cast(out, C.c_void_p))
+        return int(out[0])
 
     def nms_stats(self, B, H, W):
         out = (C.c_int64 * 4)()

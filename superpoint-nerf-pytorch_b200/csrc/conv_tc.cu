@@ -454,7 +454,8 @@ int launch_conv_tc(spn_ctx* ctx, int layer, int mode, const void* in, void* out,
 }
 
 struct TcPlan {
-  size_t a, b, feat, head, total;  // bytes
+  size_t a, b, feat, head, total;  // region sizes in bytes (each followed by a kSpnGap guard gap)
+  size_t off_b, off_feat, off_head, off_logits;
 };
 TcPlan tc_plan(int B, int H, int W) {
   TcPlan p;
@@ -464,8 +465,24 @@ TcPlan tc_plan(int B, int H, int W) {
   p.feat = (size_t)B * 128 * hw / 64 * 2;
   p.head = (size_t)B * 256 * hw / 64 * 2;  // convPa / convDa out
   const size_t logits = (size_t)B * 65 * hw / 64 * 4;
-  p.total = p.a + p.b + p.feat + p.head + logits + 4096;
+  p.off_b = p.a + kSpnGap;
+  p.off_feat = p.off_b + p.b + kSpnGap;
+  p.off_head = p.off_feat + p.feat + kSpnGap;
+  p.off_logits = p.off_head + p.head + kSpnGap;
+  p.total = p.off_logits + logits + 4096;
   return p;
+}
+
+// option "ws_guard": paint the four gaps before a pass and remember them for spn_check_guards
+int paint_gaps(spn_ctx* ctx, const TcPlan& pl, cudaStream_t s) {
+  if (!ctx->opt_ws_guard) return SPN_OK;
+  ctx->guard_gaps.clear();
+  for (size_t off : {pl.off_b, pl.off_feat, pl.off_head, pl.off_logits}) {
+    char* g = ctx->ws + off - kSpnGap;
+    SPN_CUDA(cudaMemsetAsync(g, kSpnGuardByte, kSpnGap, s));
+    ctx->guard_gaps.push_back({g, kSpnGap});
+  }
+  return SPN_OK;
 }
 
 }  // namespace
@@ -569,9 +586,10 @@ int spn_tc_encoder_slots(spn_ctx* ctx, const float* d_images, const float* d_hin
   const TcPlan pl = tc_plan(B, H, W);
   int rc = spn_ensure_ws(ctx, pl.total, s);
   if (rc) return rc;
+  if ((rc = paint_gaps(ctx, pl, s))) return rc;
   char* A = ctx->ws;
-  char* Bq = A + pl.a;
-  char* F = Bq + pl.b;
+  char* Bq = A + pl.off_b;
+  char* F = A + pl.off_feat;
   const int bf = mode == SPN_MODE_BF16 ? 1 : 0;
   if (!ctx->opt_fuse_front) {
     SPN_REQUIRE(!d_hinv, "option fuse_front = 0: the unfused path takes already-warped images");
@@ -604,7 +622,7 @@ int spn_tc_encoder(spn_ctx* ctx, const float* d_images, int B, int H, int W, int
 
 int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_logits, cudaStream_t s) {
   const TcPlan pl = tc_plan(B, H, W);
-  char* head = ctx->ws + pl.a + pl.b + pl.feat;
+  char* head = ctx->ws + pl.off_head;
   int rc;
   if ((rc = launch_conv_tc(ctx, SPN_L_CONVPA, mode, ctx->feat, head, B, H / 8, W / 8, true, false, 0, s))) return rc;
   return launch_conv_tc(ctx, SPN_L_CONVPB, mode, head, d_logits, B, H / 8, W / 8, false, false, 1, s);
@@ -614,7 +632,7 @@ int spn_tc_detector_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_l
 int spn_tc_detector_head_fused(spn_ctx* ctx, int B, int H, int W, int mode, const uint8_t* d_mask, float* d_logits, float* d_prob,
                                cudaStream_t s) {
   const TcPlan pl = tc_plan(B, H, W);
-  char* head = ctx->ws + pl.a + pl.b + pl.feat;
+  char* head = ctx->ws + pl.off_head;
   int rc;
   if ((rc = launch_conv_tc(ctx, SPN_L_CONVPA, mode, ctx->feat, head, B, H / 8, W / 8, true, false, 0, s))) return rc;
   return spn_launch_head_tc(ctx, mode, head, B, H / 8, W / 8, d_mask, d_logits, d_prob, s);
@@ -622,7 +640,7 @@ int spn_tc_detector_head_fused(spn_ctx* ctx, int B, int H, int W, int mode, cons
 
 int spn_tc_descriptor_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d_desc_raw, cudaStream_t s) {
   const TcPlan pl = tc_plan(B, H, W);
-  char* head = ctx->ws + pl.a + pl.b + pl.feat;
+  char* head = ctx->ws + pl.off_head;
   int rc;
   if ((rc = launch_conv_tc(ctx, SPN_L_CONVDA, mode, ctx->feat, head, B, H / 8, W / 8, true, false, 0, s))) return rc;
   return launch_conv_tc(ctx, SPN_L_CONVDB, mode, head, d_desc_raw, B, H / 8, W / 8, false, false, 1, s);
@@ -630,7 +648,7 @@ int spn_tc_descriptor_head(spn_ctx* ctx, int B, int H, int W, int mode, float* d
 
 float* spn_tc_logits_scratch(spn_ctx* ctx, int B, int H, int W) {
   const TcPlan pl = tc_plan(B, H, W);
-  return (float*)(ctx->ws + pl.a + pl.b + pl.feat + pl.head);
+  return (float*)(ctx->ws + pl.off_logits);
 }
 
 // single VGG_Block through the tensor-core path with NCHW fp32 in/out (layout conversion on both sides)

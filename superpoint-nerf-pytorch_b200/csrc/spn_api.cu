@@ -21,15 +21,19 @@ static int grow(char** buf, size_t* have, size_t need, cudaStream_t s) {
   if (need <= *have) return SPN_OK;
   // growing the workspace is the one place that synchronises (first call with a larger shape)
   SPN_CUDA(cudaStreamSynchronize(s));
-  if (*buf) SPN_CUDA(cudaFree(*buf));
+  if (*buf) SPN_CUDA(cudaFree(*buf - kSpnGuard));
   *buf = nullptr;
   *have = 0;
   const size_t sz = (need + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
-  cudaError_t e = cudaMalloc((void**)buf, sz);
+  char* base = nullptr;
+  cudaError_t e = cudaMalloc((void**)&base, sz + 2 * kSpnGuard);
   if (e != cudaSuccess) {
-    spn_set_error("cudaMalloc(%zu) failed: %s", sz, cudaGetErrorString(e));
+    spn_set_error("cudaMalloc(%zu) failed: %s", sz + 2 * kSpnGuard, cudaGetErrorString(e));
     return SPN_E_NOMEM;
   }
+  SPN_CUDA(cudaMemsetAsync(base, kSpnGuardByte, kSpnGuard, s));                 // guard bands (spn_check_guards)
+  SPN_CUDA(cudaMemsetAsync(base + kSpnGuard + sz, kSpnGuardByte, kSpnGuard, s));
+  *buf = base + kSpnGuard;
   *have = sz;
   return SPN_OK;
 }
@@ -78,8 +82,8 @@ extern "C" int spn_destroy(spn_ctx* ctx) {
     for (auto& p : L.w16f) if (p) cudaFree(p);
     if (L.w16x) cudaFree(L.w16x);
   }
-  if (ctx->ws) cudaFree(ctx->ws);
-  if (ctx->aux) cudaFree(ctx->aux);
+  if (ctx->ws) cudaFree(ctx->ws - kSpnGuard);
+  if (ctx->aux) cudaFree(ctx->aux - kSpnGuard);
   delete ctx;
   return SPN_OK;
 }
@@ -88,14 +92,48 @@ extern "C" int spn_set_option(spn_ctx* ctx, const char* name, int value) {
   SPN_REQUIRE(ctx && name, "spn_set_option: null pointer");
   struct { const char* n; int* v; } opts[] = {{"fold", &ctx->opt_fold}, {"fold_hybrid", &ctx->opt_fold_hybrid}, {"fuse_front", &ctx->opt_fuse_front},
                                                {"fuse_head", &ctx->opt_fuse_head}, {"pdl", &ctx->opt_pdl},
-                                               {"front_variant", &ctx->opt_front_variant}, {"front_pair", &ctx->opt_front_pair}};
+                                               {"front_variant", &ctx->opt_front_variant}, {"front_pair", &ctx->opt_front_pair},
+                                               {"ws_guard", &ctx->opt_ws_guard}};
   for (auto& o : opts)
     if (!strcmp(o.n, name)) { *o.v = value; return SPN_OK; }
-  spn_set_error("spn_set_option: unknown option '%s' (fold, fold_hybrid, fuse_front, fuse_head, pdl, front_pair)", name);
+  spn_set_error("spn_set_option: unknown option '%s' (fold, fold_hybrid, fuse_front, fuse_head, pdl, front_pair, ws_guard)", name);
   return SPN_E_INVALID;
 }
 
 extern "C" int64_t spn_launch_count(spn_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+namespace {
+__global__ void count_guard_damage_kernel(const unsigned char* __restrict__ p, size_t n, unsigned long long* __restrict__ bad) {
+  unsigned local = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    local += p[i] != (unsigned char)kSpnGuardByte;
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(bad, (unsigned long long)local);
+}
+}  // namespace
+
+// Counts the guard bytes that no longer hold the pattern: the bands around the workspace and the scratch buffer, and
+// (option "ws_guard") the gaps between the regions the last encoder pass carved.  Synchronises the device.
+extern "C" int spn_check_guards(spn_ctx* ctx, int64_t* h_bad) {
+  SPN_REQUIRE(ctx && h_bad, "spn_check_guards: null pointer");
+  SpnDeviceGuard guard(ctx->device);
+  unsigned long long* d_bad = nullptr;
+  SPN_CUDA(cudaDeviceSynchronize());
+  SPN_CUDA(cudaMalloc((void**)&d_bad, sizeof(*d_bad)));
+  SPN_CUDA(cudaMemset(d_bad, 0, sizeof(*d_bad)));
+  std::vector<std::pair<const char*, size_t>> spans;
+  if (ctx->ws) { spans.push_back({ctx->ws - kSpnGuard, kSpnGuard}); spans.push_back({ctx->ws + ctx->ws_bytes, kSpnGuard}); }
+  if (ctx->aux) { spans.push_back({ctx->aux - kSpnGuard, kSpnGuard}); spans.push_back({ctx->aux + ctx->aux_bytes, kSpnGuard}); }
+  if (ctx->opt_ws_guard)
+    for (auto& g : ctx->guard_gaps) spans.push_back({g.first, g.second});
+  for (auto& sp : spans) count_guard_damage_kernel<<<32, 256>>>((const unsigned char*)sp.first, sp.second, d_bad);
+  unsigned long long bad = 0;
+  cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) { spn_set_error("spn_check_guards: %s", cudaGetErrorString(e)); return SPN_E_CUDA; }
+  *h_bad = (int64_t)bad;
+  return SPN_OK;
+}
 
 extern "C" int spn_profile_enable(spn_ctx* ctx, int enable) {
   SPN_REQUIRE(ctx, "spn_profile_enable: null ctx");

@@ -67,6 +67,8 @@ struct spn_ctx {
   int opt_pdl = 1;          // programmatic dependent launch along the tensor-core chain
   int opt_front_variant = 0;  // diagnostic build only (tools/front_probe.py)
   int opt_front_pair = 0;   // fused front end as a 2-CTA cluster with cta_group::2 MMAs (front2_tc.cu)
+  int opt_ws_guard = 0;     // paint the gaps between the carved workspace regions before every encoder pass (spn_check_guards)
+  std::vector<std::pair<char*, size_t>> guard_gaps;   // the gaps painted by the last pass
 };
 
 void spn_set_error(const char* fmt, ...);
@@ -137,6 +139,12 @@ inline cudaError_t spn_launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid,
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Both growable buffers carry a kSpnGuard-byte band of kSpnGuardByte before and after the usable range (painted when the
+// buffer is allocated); the tensor-core workspace plan leaves kSpnGap bytes between its regions.  No kernel may ever
+// write there: spn_check_guards counts the bytes that changed (the in-repo substitute for compute-sanitizer, which is
+// closed on the GPU pool).
+constexpr size_t kSpnGuard = 64 * 1024, kSpnGap = 4096;
+constexpr int kSpnGuardByte = 0xA5;
 int spn_ensure_ws(spn_ctx* ctx, size_t bytes, cudaStream_t s);
 int spn_ensure_aux(spn_ctx* ctx, size_t bytes, cudaStream_t s);
 

@@ -249,6 +249,41 @@ def test_hybrid_fold_option(sp_model, name, shape):
     assert rel_err(a, b) < 2e-3      # same operands, the kx = 2 term is summed inside the accumulator instead of after it
 
 
+def test_workspace_guard_bands_stay_intact():
+    """In-repo substitute for compute-sanitizer (closed on the GPU pool): the workspace and the scratch buffer carry 64 KB
+    guard bands, option ws_guard paints the gaps between the carved activation regions before every pass; after plain
+    forwards, fused homography-adaptation passes (ragged sizes, several chunkings), NMS with and without top-k and the
+    aggregate, no guard byte may have changed."""
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import HomographyAdaptation
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    c = copy.deepcopy(SP_MODEL)
+    c["precision"] = "f16"
+    m = get_model(c, "cuda").eval()
+    m.load_state_dict(O.make_state_dict("superpoint", seed=2, logit_gain=8.0))
+    ctx = m.native()
+    ctx.set_option("ws_guard", 1)
+    try:
+        for (b, h, w) in [(1, 8, 8), (3, 40, 72), (2, 120, 160), (1, 240, 320), (5, 64, 72)]:
+            x = torch.rand((b, 1, h, w), device="cuda")
+            m(x)
+            m(x, keypoints=True)
+            assert ctx.check_guards() == 0, (b, h, w)
+        ha = {"num": 7, "aggregation": "sum", "filter_counts": 0, "valid_border_margin": 3, "sampler": "device", "seed": 3,
+              "params": {"translation": True, "rotation": True, "scaling": True, "perspective": True, "scaling_amplitude": 0.2,
+                         "perspective_amplitude_x": 0.2, "perspective_amplitude_y": 0.2, "allow_artifacts": True,
+                         "patch_ratio": 0.85, "max_angle": 1.57}}
+        for mf in (3, 8, 400):
+            eng = HomographyAdaptation({"homography_adaptation": dict(ha, max_forwards=mf), "model": c}, m, "cuda")
+            for (b, h, w) in [(2, 40, 72), (3, 120, 160), (1, 240, 320)]:
+                heat, _ = eng.heatmaps(torch.rand((b, 1, h, w), device="cuda"))
+                eng.keypoints(heat)
+                assert ctx.check_guards() == 0, (mf, b, h, w)
+        ctx.box_nms(torch.rand((1, 64, 64), device="cuda"), 4.0, 0.1, 0.5, 0, det_thresh=0.5, want_map=True)
+        assert ctx.check_guards() == 0
+    finally:
+        ctx.set_option("ws_guard", 0)
+
+
 def test_fast_path_is_deterministic_across_chunkings():
     """The tensor-core kernels are chained with programmatic dependent launch and reuse two activation buffers from
     chunk to chunk: the result must not depend on how the homography slots are chunked, nor vary from run to run
