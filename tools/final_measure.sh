@@ -16,7 +16,7 @@ timeout 200 python bench.py --precision f16x3 --images-per-step 32 --steps 10 --
 CMD="python bench.py --images-per-step 2 --steps 1 --warmup 3 --max-forwards 100 --no-cpu-baseline"
 timeout 200 $CMD > $O/ncu_plain.log 2>&1 && \
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/r2_launches.csv $CMD > $O/ncu1.log 2>&1
-timeout 600 ncu --set full --clock-control none -s 78 -c 30 -o /tmp/r2_prof $CMD > $O/ncu2.log 2>&1
+timeout 600 ncu --set full --clock-control none -s 81 -c 30 -o /tmp/r2_prof $CMD > $O/ncu2.log 2>&1
 ncu -i /tmp/r2_prof.ncu-rep --page raw --csv > $O/r2_prof_raw.csv 2> $O/ncu2b.log
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"front_tc" -s 2 -c 1 -o $O/r2_prof_front_final $CMD > $O/ncu4.log 2>&1
 ls -la $O/*.csv $O/*.ncu-rep | tail -5
