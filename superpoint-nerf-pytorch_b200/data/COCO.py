@@ -13,7 +13,7 @@ import torch
 from torch.utils.data import Dataset
 
 from .. import settings
-from .preprocessing import ratio_preserving_resize
+from .preprocessing import pin_host as _pin, ratio_preserving_resize
 
 
 class COCO(Dataset):
@@ -43,11 +43,12 @@ class COCO(Dataset):
         """COCO.py:61-64, stopping at the decoded uint8 (H0,W0) image (the float conversion is fused into the resize)."""
         import torchvision
         data = torchvision.io.read_file(image)
-        return torchvision.io.decode_image(data, torchvision.io.ImageReadMode.GRAY).squeeze(0)
+        return _pin(torchvision.io.decode_image(data, torchvision.io.ImageReadMode.GRAY).squeeze(0))
 
     def ratio_preserving_resize(self, image, normalize=False):
         """COCO.py:66-76 on the device: (H0,W0) uint8 / fp32 -> (H,W) fp32."""
-        return ratio_preserving_resize(image.to(self.device, non_blocking=True), self.config["preprocessing"]["resize"], normalize=normalize)
+        # host images are uploaded by the module function on its side stream (never on the consumer's stream)
+        return ratio_preserving_resize(image, self.config["preprocessing"]["resize"], normalize=normalize, device=self.device)
 
     def decode(self, index):
         """Host part of ``__getitem__`` (thread-safe): -> (uint8 image, name)."""

@@ -8,7 +8,7 @@ import torch
 from torch.utils.data import Dataset
 
 from .. import settings
-from .preprocessing import adapt_homography_to_resize, ratio_preserving_resize
+from .preprocessing import pin_host as _pin, adapt_homography_to_resize, ratio_preserving_resize
 
 
 class HPatches(Dataset):
@@ -42,10 +42,11 @@ class HPatches(Dataset):
     def read_image(self, image):
         """HPatches.py:58-60, stopping at the decoded uint8 image."""
         import cv2
-        return torch.from_numpy(cv2.imread(image, cv2.IMREAD_GRAYSCALE))
+        return _pin(torch.from_numpy(cv2.imread(image, cv2.IMREAD_GRAYSCALE)))
 
     def ratio_preserving_resize(self, image, normalize=False):
-        return ratio_preserving_resize(image.to(self.device, non_blocking=True), self.config["preprocessing"]["resize"], normalize=normalize)
+        # host images are uploaded by the module function on its side stream (never on the consumer's stream)
+        return ratio_preserving_resize(image, self.config["preprocessing"]["resize"], normalize=normalize, device=self.device)
 
     def adapt_homography_to_resize(self, homographies):
         """HPatches.py:74-100."""

@@ -29,14 +29,50 @@ def resize_geometry(src_shape, target):
     return nh, nw, top, left
 
 
-def ratio_preserving_resize(image, target, normalize=True):
-    """image (H0,W0) uint8 or fp32 (CUDA, or CPU - it is uploaded) -> (H,W) fp32 CUDA, /255 when ``normalize``."""
+_upload_streams = {}
+
+
+def pin_host(image):
+    """Decoded host image -> page-locked copy (torch's caching pinned allocator; called on the decode threads) so that the
+    upload is a real asynchronous DMA instead of a staged copy the issuing thread has to wait for."""
+    try:
+        return image.pin_memory() if torch.cuda.is_available() and not image.is_cuda else image
+    except RuntimeError:
+        return image
+
+
+def _upload_stream(device):
+    """One side stream per GPU for the loader's uploads."""
+    key = torch.device(device).index
+    if key not in _upload_streams:
+        _upload_streams[key] = torch.cuda.Stream(device=device)
+    return _upload_streams[key]
+
+
+def ratio_preserving_resize(image, target, normalize=True, device=None):
+    """image (H0,W0) uint8 or fp32 (CUDA, or CPU - it is uploaded) -> (H,W) fp32 CUDA, /255 when ``normalize``.
+
+    A host image is uploaded and resized on a side stream: a copy from pageable memory blocks the calling thread until
+    the stream it was issued on reaches it, and on the consumer's stream that is after every kernel of the export group
+    already in flight (the loader then runs in lock step with the GPU instead of ahead of it).  The consumer's stream
+    only waits for the side stream's event.  Pinned host images (the datasets pin them on their decode threads) make
+    the upload truly asynchronous."""
     if image.dim() == 3 and image.shape[0] == 1:
         image = image[0]
-    if not image.is_cuda:
-        image = image.cuda(non_blocking=True)
     nh, nw, top, left = resize_geometry(image.shape, target)
-    return get_context(image.device).resize_crop(image, nh, nw, top, left, int(target[0]), int(target[1]), 255.0 if normalize else 1.0)
+    scale = 255.0 if normalize else 1.0
+    if image.is_cuda:
+        return get_context(image.device).resize_crop(image, nh, nw, top, left, int(target[0]), int(target[1]), scale)
+    dev = torch.device(device) if device is not None else torch.device("cuda")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    cur, side = torch.cuda.current_stream(dev), _upload_stream(dev)
+    with torch.cuda.stream(side):
+        image = image.to(dev, non_blocking=True)
+        out = get_context(dev).resize_crop(image, nh, nw, top, left, int(target[0]), int(target[1]), scale)
+    out.record_stream(cur)
+    cur.wait_stream(side)
+    return out
 
 
 def adapt_homography_to_resize(homography, image_shape, warped_image_shape, target):

@@ -68,13 +68,40 @@ def main():
         n_warm = max(64, 2 * args.images_per_launch)   # two full groups: workspace, pinned staging and allocator pools at their final size
         ExportDetections(warm, model, [b for _, b in zip(range(n_warm), loader)], "training", True, "cuda")
         torch.cuda.synchronize()
+        # where the export loop's host thread spends its time: waiting for the GPU (good), launching, saving, or in the loader
+        acc = {"wait_gpu": 0.0, "launch": 0.0, "finish_total": 0.0}
+        from superpoint_nerf_pytorch_b200.engine_solvers import export as E
+        o_wait, o_launch, o_finish = E.HomographyAdaptation.keypoints_wait, E.ExportDetections._launch, E.ExportDetections._finish
+
+        def timed(fn, key):
+            def w(*a, **k):
+                t = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    acc[key] += time.perf_counter() - t
+            return w
+
+        def wait_split(self, handle):
+            t = time.perf_counter()
+            handle["event"].synchronize()
+            acc["wait_gpu"] += time.perf_counter() - t
+            return o_wait(self, handle)
+
+        E.HomographyAdaptation.keypoints_wait = wait_split
+        E.ExportDetections._launch = timed(o_launch, "launch")
+        E.ExportDetections._finish = timed(o_finish, "finish_total")
         t0 = time.perf_counter()
         ExportDetections(cfg, model, loader, "training", True, "cuda")
         torch.cuda.synchronize()
         t_exp = time.perf_counter() - t0
+        E.HomographyAdaptation.keypoints_wait, E.ExportDetections._launch, E.ExportDetections._finish = o_wait, o_launch, o_finish
+        acc["loader_and_loop"] = t_exp - acc["launch"] - acc["finish_total"]
+        acc["save_and_convert"] = acc["finish_total"] - acc["wait_gpu"]
         files = len(list(Path(tmp, "exper", "outputs", "loader_bench", "training").glob("*.npy")))
         print(json.dumps({"images": n, "loader_only_img_per_s": n / t_load, "export_with_loader_img_per_s": files / t_exp,
-                          "files_written": files, "workers": loader.workers, "images_per_launch": args.images_per_launch,
+                          "files_written": files, "host_thread_seconds": {k: round(v, 3) for k, v in acc.items()}, "seconds": round(t_exp, 3),
+                          "workers": loader.workers, "images_per_launch": args.images_per_launch,
                           "max_forwards": args.max_forwards, "jpeg": "640x480 q90 -> 240x320",
                           "note": "export = decode (host threads) + resize kernel + HA x100 (f16) + NMS + .npy per image"}))
     finally:
