@@ -51,6 +51,10 @@ constexpr int kTurnTap = SPN_TURN_TAP;               // the issue turn passes to
 #define SPN_POLL_NS 0
 #endif
 constexpr uint32_t kPollNs = SPN_POLL_NS;             // back-off between barrier polls of the producer / epilogue roles
+#ifndef SPN_MMA1_AHEAD
+#define SPN_MMA1_AHEAD 3
+#endif
+constexpr int kAhead = SPN_MMA1_AHEAD;               // block_1's MMAs are issued this many tiles ahead of block_2's (2 or 3; 3 D1 buffers)
 #ifndef SPN_P_GROUPS
 #define SPN_P_GROUPS 4
 #endif
@@ -180,9 +184,11 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       __syncwarp();
     };
 
-    // Per issuer: MMA1(par) | MMA2(par) MMA1(par+2) | MMA2(par+2) MMA1(par+4) | ...  block_1 of a tile is issued two
-    // tiles ahead of its block_2, so E1 turns D1(i+1) into slab(i+1) while MMA2(i) runs and P has two tile times for A1.
+    // Per issuer: MMA2(i) is followed by MMA1(i + kAhead).  block_1 of a tile is issued kAhead = 3 tiles ahead of its
+    // block_2 (as far as the three D1 buffers and the four slab stages allow), so E1 has two tile times to turn D1 into
+    // the slab (2117 -> 2069 cycles per tile against two tiles ahead).
     if ((int)(blockIdx.x + par * gridDim.x) < n_tiles) issue_mma1(par);
+    if (kAhead == 3 && par == 0 && (int)(blockIdx.x + 2 * gridDim.x) < n_tiles) issue_mma1(2);
     for (int i = par, t = blockIdx.x + par * gridDim.x; t < n_tiles; t += 2 * gridDim.x, i += 2) {
       const int stage = i % kStages, acc = i & 1;
       const uint32_t sph = (uint32_t)(i / kStages) & 1u, aph = (uint32_t)(i >> 1) & 1u;
@@ -221,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
         if (kTurnTap >= 9 || (kTurnTap >= 0 && (DBG & 128))) mbar_arrive(&bar_turn[par ^ 1]);
       }
       __syncwarp();
-      if (t + 2 * (int)gridDim.x < n_tiles) issue_mma1(i + 2);
+      if (t + kAhead * (int)gridDim.x < n_tiles) issue_mma1(i + kAhead);   // kAhead == 3: the other issuer's next tile
     }
   } else if (warp >= 10) {
     // ===================== P: warped patch + im2col operand of block_1 =====================
