@@ -10,15 +10,17 @@
 //   P  warps 10-17  bilinear-sample the 12 x 20 warped-image patch, build block_1's im2col operand A1
 //                   (256 rows = the 10 x 18 halo pixels (180 used), K = 9 taps padded to 16, fp16) in SMEM;
 //                   kPGroups groups of warps that take tiles round robin
-//   M  warp 1       MMA1: D1 = A1 . W1 (2 x M128 N64 K16) into TMEM, issued one tile AHEAD of
-//                   MMA2: D2 += slab(tap) . W2(tap) (36 x M128 N64 K16, weights resident in SMEM)
+//   M  warps 0, 1   two issuers, one per tile parity, taking turns (bar_turn).  MMA1: D1 = A1 . W1 (2 x M128 N64 K16)
+//                   into TMEM, issued kAhead = 3 tiles AHEAD of
+//                   MMA2: D2 += slab(tap) . W2(tap) (36 x M128 N64 K16, weights resident in SMEM), rolled tap loop
 //   E1 warps 6-9    D1 (bias already added through A1's ones columns, rows outside the image exactly 0 = block_2's
 //                   zero padding) -> ReLU -> fp16 -> the slab
 //                   [chunk][halo row][halo col][8] that MMA2's nine shifted descriptors read
-//   E2 warps 2-5    D2 (bias2 added by one extra MMA against a constant ones operand) -> 2x2 max-pool (two shfl.xor)
-//                   -> ReLU -> 16-byte C8 stores
-//   warp 0          weight loader (cp.async.bulk)
-// All hand-offs are mbarriers (generic-proxy SMEM writes are published to the tensor core with fence.proxy.async).
+//   E2 warps 2-5    D2 (bias2 added by one extra MMA against a constant ones operand) -> fp16 + ReLU in one cvt -> 2x2
+//                   max-pool (two shfl.xor) -> 16-byte C8 stores
+//   warp 0          also the weight loader (cp.async.bulk)
+// All hand-offs are mbarriers with one arrival per warp (generic-proxy SMEM writes are published to the tensor core
+// with fence.proxy.async).  How the role balance was found: DESIGN.md section 3.2, tools/front_probe_cycles.sh.
 #include "spn_common.cuh"
 #include "spn_geom.cuh"
 #include "tc_ptx.cuh"
