@@ -21,6 +21,8 @@ class COCO(Dataset):
         super().__init__()
         self.config = data_config
         self.device = device
+        if torch.cuda.is_available() and torch.device(device).type == "cuda" and torch.device(device).index is None:
+            self.device = f"cuda:{torch.cuda.current_device()}"   # resolved here: decode threads start with device 0 current
         self.action = "training" if task == "training" else "validation" if task == "validation" else "test"
         aug = data_config.get("augmentation", {})
         if data_config.get("has_labels") or data_config.get("warped_pair") or any(aug.get(k, {}).get("enable") for k in aug):
@@ -43,7 +45,7 @@ class COCO(Dataset):
         """COCO.py:61-64, stopping at the decoded uint8 (H0,W0) image (the float conversion is fused into the resize)."""
         import torchvision
         data = torchvision.io.read_file(image)
-        return _pin(torchvision.io.decode_image(data, torchvision.io.ImageReadMode.GRAY).squeeze(0))
+        return _pin(torchvision.io.decode_image(data, torchvision.io.ImageReadMode.GRAY).squeeze(0), self.device)
 
     def ratio_preserving_resize(self, image, normalize=False):
         """COCO.py:66-76 on the device: (H0,W0) uint8 / fp32 -> (H,W) fp32."""

@@ -16,6 +16,8 @@ class HPatches(Dataset):
         super().__init__()
         self.config = data_config
         self.device = device
+        if torch.cuda.is_available() and torch.device(device).type == "cuda" and torch.device(device).index is None:
+            self.device = f"cuda:{torch.cuda.current_device()}"   # resolved here: decode threads start with device 0 current
         self.samples = self._init_dataset()
 
     def _init_dataset(self):
@@ -42,7 +44,7 @@ class HPatches(Dataset):
     def read_image(self, image):
         """HPatches.py:58-60, stopping at the decoded uint8 image."""
         import cv2
-        return _pin(torch.from_numpy(cv2.imread(image, cv2.IMREAD_GRAYSCALE)))
+        return _pin(torch.from_numpy(cv2.imread(image, cv2.IMREAD_GRAYSCALE)), self.device)
 
     def ratio_preserving_resize(self, image, normalize=False):
         # host images are uploaded by the module function on its side stream (never on the consumer's stream)

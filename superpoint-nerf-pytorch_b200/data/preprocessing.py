@@ -32,11 +32,17 @@ def resize_geometry(src_shape, target):
 _upload_streams = {}
 
 
-def pin_host(image):
+def pin_host(image, device=None):
     """Decoded host image -> page-locked copy (torch's caching pinned allocator; called on the decode threads) so that the
-    upload is a real asynchronous DMA instead of a staged copy the issuing thread has to wait for."""
+    upload is a real asynchronous DMA instead of a staged copy the issuing thread has to wait for.  ``device``: the GPU
+    the loader feeds - a new thread's current device is 0, and pinning there would create a context on GPU 0 in every
+    rank of a multi-GPU export."""
+    if not torch.cuda.is_available() or image.is_cuda:
+        return image
     try:
-        return image.pin_memory() if torch.cuda.is_available() and not image.is_cuda else image
+        dev = torch.device(device) if device is not None else torch.device("cuda")
+        with torch.cuda.device(dev if dev.index is not None else torch.cuda.current_device()):
+            return image.pin_memory()
     except RuntimeError:
         return image
 
