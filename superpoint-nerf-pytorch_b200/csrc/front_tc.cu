@@ -44,7 +44,11 @@ constexpr int kA1Rows = 256;
 constexpr int kA1Bytes = 2 * kA1Rows * 16;            // [chunk 2][row 256][8 halfs]
 constexpr int kStages = 4;
 constexpr int kNA1 = 3;                               // D1 buffers (TMEM): MMA1 runs two tiles ahead of MMA2
-constexpr int kThreads = 576;                         // 18 warps
+#ifndef SPN_E2_GROUPS
+#define SPN_E2_GROUPS 1
+#endif
+constexpr int kE2Groups = SPN_E2_GROUPS;              // block_2 epilogue groups (2: warps 18-21 take the odd tiles)
+constexpr int kThreads = 576 + (kE2Groups - 1) * 128;  // 18 (22) warps
 #ifndef SPN_TURN_TAP
 #define SPN_TURN_TAP 9
 #endif
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       __syncwarp();
       if (t + kAhead * (int)gridDim.x < n_tiles) issue_mma1(i + kAhead);   // kAhead == 3: the other issuer's next tile
     }
-  } else if (warp >= 10) {
+  } else if (warp >= 10 && warp < 18) {
     // ===================== P: warped patch + im2col operand of block_1 =====================
     // kPGroups groups of warps take tiles round robin.  A tile's P work is one long dependent chain (coordinates ->
     // four L2 loads -> interpolation -> patch -> barrier -> im2col rows -> fence), ~2300 cycles when all eight warps
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a1_full[b]);   // one arrival per warp (see the note on shared-memory traffic above)
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 6 && warp < 10) {
     // ===================== E1: block_1 epilogue -> block_2's input slab =====================
     const int q = warp & 3;
     int i = 0;
@@ -366,8 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) front_tc_kernel(const FrontParams
     const int q = warp & 3;
     const int g = q * 4 + (lane >> 3), r = lane & 7;
     const int Ho = p.H >> 1, Wo = p.W >> 1;
-    int i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    const int e2g = warp >= 18 ? 1 : 0;   // with two groups each owns one accumulator / tile parity
+    for (int i = e2g, t = blockIdx.x + e2g * gridDim.x; t < n_tiles; t += kE2Groups * gridDim.x, i += kE2Groups) {
       const int acc = i & 1;
       const uint32_t aph = (uint32_t)(i >> 1) & 1u;
       const int ls = fast_div(t, p.magic_tpi), rr = t - ls * tiles_per_img;
