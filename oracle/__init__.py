@@ -10,6 +10,10 @@ reference algorithm for the path named in SURVEY.md section 8, each function cit
 reference file:line it follows (paths relative to
 ``/root/reference/superpoint/superpoint/``).
 
+Modules: ``spn_oracle`` (model forward, box_nms, sampler, homography adaptation, pre-processing, detector labels),
+``eval_oracle`` (the rows SURVEY.md section 8f adds: repeatability, keep_shared_points, cross-checked matching, the
+NeRF re-projection step), ``kornia_shim`` (kornia 0.7.0 restated), ``nms_ref.c`` (greedy NMS in plain C).
+
 Pinning status
 --------------
 * The reference ships no tests, golden vectors or fixtures for this path

@@ -234,8 +234,9 @@ class ExportDetections:
         for k, im in enumerate(imgs):
             buf[k].copy_(im[0])
         dev = buf.to(self.device, non_blocking=True)
-        slot["ev"] = torch.cuda.Event()
-        slot["ev"].record()
+        with torch.cuda.device(dev.device):            # the event goes on the stream that carries the copy
+            slot["ev"] = torch.cuda.Event()
+            slot["ev"].record(torch.cuda.current_stream(dev.device))
         return dev
 
     def _launch(self, group, index):
@@ -473,9 +474,13 @@ class ExportNeRFDetections:
                                                data["raw"]["input_rotation"][j], data["raw"]["input_translation"][j]))
                 mean = torch.stack(maps).sum(0) / float(len(maps))
                 ctx = self.model.native()
+                cap = min(mean.numel(), 16384)
                 r = ctx.box_nms(mean.unsqueeze(0), float(dh["nms"]), 0.1, float(dh["det_thresh"]), int(dh["top_k"]),
-                                det_thresh=float(dh["det_thresh"]), want_map=False, max_kp=min(mean.numel(), 16384))
+                                det_thresh=float(dh["det_thresh"]), want_map=False, max_kp=cap)
                 n = int(r["kp_count"][0])
+                if n > cap:                            # more keypoints than the list holds: redo with the true size
+                    r = ctx.box_nms(mean.unsqueeze(0), float(dh["nms"]), 0.1, float(dh["det_thresh"]), int(dh["top_k"]),
+                                    det_thresh=float(dh["det_thresh"]), want_map=False, max_kp=n)
                 np.save(save_path, r["kp"][0, :n].cpu().numpy().astype(np.int64))
 
 

@@ -38,7 +38,9 @@ def keep_shared_points(keypoint_map, H, keep_k_points=1000, device="cuda"):
 def _lookup(data, key_dense, key_sparse, key_kp, keypoints):
     if key_dense in data:
         return np.ascontiguousarray(data[key_dense][keypoints[:, 0], keypoints[:, 1]], dtype=np.float32)
-    kp = np.asarray(data[key_kp]).astype(np.int64)                    # sparse layout: descriptors stored at their keypoints
+    kp = np.asarray(data[key_kp]).astype(np.int64).reshape(-1, 2)     # sparse layout: descriptors stored at their keypoints
+    if len(keypoints) == 0:
+        return np.zeros((0, np.asarray(data[key_sparse]).shape[-1]), np.float32)
     w = int(kp[:, 1].max()) + 1
     index = {int(r) * w + int(c): i for i, (r, c) in enumerate(kp)}
     rows = [index[int(r) * w + int(c)] for r, c in keypoints]

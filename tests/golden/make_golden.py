@@ -397,6 +397,36 @@ def main():
     np.savez_compressed(OUT / "nerf_export.npz", **nf)
     print("nerf export keypoints", {k: v.shape for k, v in nf.items() if k.startswith("view")})
 
+    # ---- 11. ExportNeRFDetections.step (export.py:246-300) in isolation: a stub model returns a fixed heatmap, so the
+    #          golden holds exactly what NMS -> nonzero -> warp_points_NeRF -> filter_points -> the splat loop produce ----
+    ns = {}
+    stepper = object.__new__(refexport.ExportNeRFDetections)
+    stepper.config = {"model": {"detector_head": {"nms": 4, "det_thresh": 0.05, "top_k": 0}}}
+    stepper.device = "cpu"
+    ns["nms"], ns["det_thresh"], ns["top_k"] = np.array(4), np.array(0.05), np.array(0)
+    for case, (bseed, nv, j, k) in enumerate([(0, 4, 0, 1), (0, 4, 2, 3), (1, 5, 4, 0)]):
+        bt = make_nerf_batch(bseed, n_views=nv)
+        h, w = bt["raw"]["image"].shape[-2:]
+        rs = np.random.RandomState(900 + case)
+        heat = np.zeros((h, w), np.float32)
+        n_det = 150
+        ry, rx = rs.randint(0, h, n_det), rs.randint(0, w, n_det)          # includes border detections (single-pixel copies)
+        heat[ry, rx] = rs.uniform(0.06, 1.0, n_det).astype(np.float32)
+        heat += rs.uniform(0.0, 0.01, (h, w)).astype(np.float32)           # background below det_thresh (patch contents)
+        heat_t = torch.from_numpy(heat)
+        stepper.model = lambda x, _h=heat_t: {"detector_output": {"prob_heatmap": _h.unsqueeze(0)}}
+        probs0 = torch.zeros((1, 1, h, w))
+        p_out, _ = stepper.step(bt["raw"]["image"][k:k + 1], probs0, torch.ones((1, 1, h, w)),
+                                bt["raw"]["input_rotation"][j], bt["raw"]["input_translation"][j],
+                                bt["raw"]["input_rotation"][k], bt["raw"]["input_translation"][k],
+                                bt["raw"]["input_depth"][k], bt["camera_intrinsic_matrix"][j])
+        ns[f"case{case}"] = np.array([bseed, nv, j, k])
+        ns[f"heat{case}"] = heat
+        ns[f"splat{case}"] = p_out[0, 1].numpy()
+    ns["n"] = np.array(3)
+    np.savez_compressed(OUT / "nerf_step.npz", **ns)
+    print("nerf step splats", [int((ns[f"splat{c}"] > 0).sum()) for c in range(3)])
+
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

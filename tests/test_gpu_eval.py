@@ -134,3 +134,43 @@ def test_select_keypoints_full_size_properties():
     dense = torch.rand((1, 200, 200), device="cuda") + 0.1           # 40000 candidates > 16384: must be flagged
     _, _, c2 = ctx.select_keypoints(dense, keep_k=10)
     assert int(c2[1]) == 40000 > ctx.SELECT_CAP
+
+
+def test_repeatability_vs_oracle_fresh_pairs_and_degenerate_maps():
+    """Batched spn_select_keypoints + spn_repeatability_counts against the CPU oracle (oracle/eval_oracle.py, pinned to the
+    reference by tests/test_oracle_golden.py) on pairs the goldens do not hold: 240x320 (the repeatability config's size),
+    several k / thresholds, one pair without detections in the first image and one without any."""
+    from oracle import eval_oracle as O
+    from superpoint_nerf_pytorch_b200.evaluations import detector_evaluation as E
+    pairs = [make_eval_pair(s, h=240, w=320, n_pts=900) for s in (11, 12, 13)]
+    empty_first = dict(pairs[0], prob=np.zeros_like(pairs[0]["prob"]))
+    empty_both = dict(empty_first, warped_prob=np.zeros_like(pairs[0]["prob"]))
+    pairs += [empty_first, empty_both]
+    probs, warped, hs = (np.stack([p[k] for p in pairs]) for k in ("prob", "warped_prob", "homography"))
+    for kk, thr in ((300, 3), (1000, 1), (25, 5)):
+        rep, counts = E.repeatability_of_pairs(probs, warped, hs, kk, thr)
+        for i, p in enumerate(pairs):
+            want = O.repeatability_pair(p["prob"], p["warped_prob"], p["homography"], kk, thr)
+            assert tuple(int(v) for v in counts[i]) == want[1:], (i, kk, thr, counts[i], want)
+            assert (np.isnan(rep[i]) and np.isnan(want[0])) or rep[i] == want[0], (i, kk, thr)
+
+
+def test_keep_shared_points_and_matches_vs_oracle_fresh_pairs():
+    """keep_shared_points + mutual_nn_matches against the CPU oracle at 240x320 with ~700 detections per image.  The seeds
+    are chosen so that every nearest neighbour is separated from the runner-up by > 8e-5 (fp32 rounding cannot decide a
+    match; the tensor-core distances are within ~1e-6)."""
+    from oracle import eval_oracle as O
+    from superpoint_nerf_pytorch_b200.evaluations import descriptor_evaluation as E
+    for seed in (23, 25):
+        d = make_eval_pair(seed, h=240, w=320, n_pts=900)
+        kp1 = E.keep_shared_points(d["prob"], d["homography"], 1000)
+        kp2 = E.keep_shared_points(d["warped_prob"], np.linalg.inv(d["homography"]), 1000)
+        assert np.array_equal(kp1, O.keep_shared_points(d["prob"], d["homography"], 1000))
+        assert np.array_equal(kp2, O.keep_shared_points(d["warped_prob"], np.linalg.inv(d["homography"]), 1000))
+        a, b = d["desc"][kp1[:, 0], kp1[:, 1]], d["warped_desc"][kp2[:, 0], kp2[:, 1]]
+        want_pairs, want_dist = O.mutual_nn(a, b)
+        got = E.mutual_nn_matches(a, b)
+        got_pairs = np.array([[m.queryIdx, m.trainIdx] for m in got], np.int64).reshape(-1, 2)
+        assert np.array_equal(got_pairs, want_pairs), seed
+        assert np.abs(np.array([m.distance for m in got], np.float32) - want_dist).max() < 1e-5
+        assert len(got) > 300

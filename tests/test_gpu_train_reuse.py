@@ -65,7 +65,7 @@ def test_detector_labels_vs_reference(golden):
 
 
 def test_nerf_splat_matches_sequential_loop():
-    """spn_nerf_splat vs the reference's sequential Python loop (export.py:271-283) restated in numpy, with overlapping
+    """spn_nerf_splat vs the reference's sequential Python loop (export.py:271-283) as restated by the oracle, with overlapping
     patches (order matters: later pairs overwrite) and border points (single-pixel case)."""
     import superpoint_nerf_pytorch_b200 as P
     ctx = P.get_context("cuda:0")
@@ -75,13 +75,8 @@ def test_nerf_splat_matches_sequential_loop():
     src = np.stack([rng.randint(0, H, n), rng.randint(0, W, n)], 1).astype(np.int32)
     dst = np.stack([rng.uniform(0, H - 1.001, n), rng.uniform(0, W - 1.001, n)], 1).astype(np.float32)
     dst[:6] = [[0.2, 5.7], [1.9, 9.0], [H - 1.5, 3.3], [10.5, W - 1.2], [20.0, 20.0], [20.9, 21.2]]
-    want = np.zeros((H, W), np.float32)
-    for u, w_ in zip(dst, src):
-        u0, u1, w0, w1 = int(u[0]), int(u[1]), int(w_[0]), int(w_[1])
-        if u0 <= 1 or u1 <= 1 or u0 >= H - 1 or u1 >= W - 1 or w0 <= 1 or w1 <= 1 or w0 >= H - 1 or w1 >= W - 1:
-            want[u0, u1] = prob[w0, w1]
-        else:
-            want[u0 - 1:u0 + 2, u1 - 1:u1 + 2] = prob[w0 - 1:w0 + 2, w1 - 1:w1 + 2]
+    from oracle import eval_oracle as EO
+    want = EO.nerf_splat(prob, dst, src)            # pinned to the reference's step by tests/test_oracle_golden.py
     got = ctx.nerf_splat(torch.from_numpy(prob).cuda(), torch.from_numpy(dst).cuda(), torch.from_numpy(src).cuda()).cpu().numpy()
     assert np.array_equal(got, want)
     empty = ctx.nerf_splat(torch.from_numpy(prob).cuda(), torch.zeros((0, 2), device="cuda"), torch.zeros((0, 2), dtype=torch.int32, device="cuda"))
@@ -118,3 +113,35 @@ def test_export_nerf_detections_vs_reference_golden(golden, tmp_path, monkeypatc
             assert abs(len(kp) - len(g[nm])) <= max(2, len(g[nm]) // 50), (nm, len(kp), len(g[nm]))
     print(f"NeRF export: worst keypoint agreement {worst:.4f}")
     assert worst >= 0.99
+
+
+def test_nerf_reproject_vs_reference_step_golden(golden):
+    """ExportNeRFDetections.reproject (box_nms keypoint list -> depth-aware re-projection -> spn_nerf_splat) against the
+    map ExportNeRFDetections.step of the unmodified reference produced from the same heatmap (tests/golden/nerf_step.npz).
+    The re-projection runs in CUDA fp32 (3x3 inverses and 3xN products), so a coordinate that lands within an ulp of an
+    integer may truncate differently: at most 0.5 % of the pixels may differ (measured: none)."""
+    import copy
+    from conftest import MP_MODEL, make_nerf_batch
+    from superpoint_nerf_pytorch_b200.engine_solvers.export import ExportNeRFDetections
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    g = golden("nerf_step.npz")
+    m = get_model(dict(copy.deepcopy(MP_MODEL), precision="fp32"), "cuda").eval()
+    ex = object.__new__(ExportNeRFDetections)
+    ex.model, ex.device = m, "cuda"
+    ctx = m.native()
+    det = float(g["det_thresh"])
+    worst = 0.0
+    for c in range(int(g["n"])):
+        bseed, nv, j, k = (int(v) for v in g[f"case{c}"])
+        bt = make_nerf_batch(bseed, n_views=nv)
+        raw = {kk: v.cuda() for kk, v in bt["raw"].items()}
+        heat = torch.from_numpy(g[f"heat{c}"]).cuda()
+        r = ctx.box_nms(heat[None], float(g["nms"]), 0.1, det, int(g["top_k"]), det_thresh=det, want_map=False, max_kp=4096)
+        n = int(r["kp_count"][0])
+        got = ex.reproject(heat, r["kp"][0, :n], raw["input_depth"][k], bt["camera_intrinsic_matrix"][j].cuda(),
+                           raw["input_rotation"][k], raw["input_translation"][k], raw["input_rotation"][j],
+                           raw["input_translation"][j]).cpu().numpy()
+        bad = float((got != g[f"splat{c}"]).mean())
+        worst = max(worst, bad)
+        assert bad <= 5e-3, (c, bad)
+    print(f"NeRF reproject: worst fraction of differing pixels {worst:.2e}")

@@ -270,3 +270,28 @@ def test_packed_label_reader(tmp_path):
     np.savez(tmp_path / "packed_rank001.npz", names=np.array(["z"]), keypoints=c, offsets=np.array([0, 1]), global_offset=np.array(2))
     got = load_packed_labels(tmp_path)
     assert sorted(got) == ["x", "y", "z"] and np.array_equal(got["x"], a) and got["y"].shape == (0, 2) and got["z"].dtype == np.int64
+
+
+def test_nerf_point_reprojection_mirror_matches_the_oracle(golden):
+    """data/data_utils/kp_utils.warp_points_NeRF (5x5 depth rule evaluated with pooling instead of the reference's
+    per-point Python loop) and filter_points on CPU tensors: bit-equal to the oracle restatement, which
+    tests/test_oracle_golden.py pins to the unmodified reference's ExportNeRFDetections.step."""
+    import torch
+    from conftest import make_nerf_batch
+    from oracle import eval_oracle as EO
+    from superpoint_nerf_pytorch_b200.data.data_utils.kp_utils import filter_points, warp_points_NeRF
+    rng = np.random.RandomState(2)
+    for seed, nv, j, k in ((0, 4, 1, 3), (1, 5, 0, 2)):
+        bt = make_nerf_batch(seed, n_views=nv)
+        raw = bt["raw"]
+        h, w = raw["input_depth"].shape[-2:]
+        pts = torch.from_numpy(np.unique(np.stack([rng.randint(0, h, 300), rng.randint(0, w, 300)], 1), axis=0))   # incl. borders
+        got = warp_points_NeRF(pts.to(torch.float32), raw["input_depth"][k][None], bt["camera_intrinsic_matrix"][j][None],
+                               raw["input_rotation"][k][None], raw["input_translation"][k][None], raw["input_rotation"][j][None],
+                               raw["input_translation"][j][None]).reshape(-1, 2)
+        want = EO.nerf_reproject_points(pts, raw["input_depth"][k], bt["camera_intrinsic_matrix"][j], raw["input_rotation"][k],
+                                        raw["input_translation"][k], raw["input_rotation"][j], raw["input_translation"][j])
+        assert torch.equal(got, want)
+        kept, mask = filter_points(got, (h, w), return_mask=True)
+        ok = (want[:, 0] >= 0) & (want[:, 0] < h - 1) & (want[:, 1] >= 0) & (want[:, 1] < w - 1)
+        assert torch.equal(mask, ok) and torch.equal(kept, want[ok]) and 0 < int(ok.sum()) < len(pts)

@@ -145,3 +145,52 @@ def test_detector_labels_restatement_matches_reference_loss(golden):
     assert torch.equal(O.detector_loss(logits, kmap, valid, include_mask=True), torch.as_tensor(g["loss_ref_masked"]))
     labels, cells, _ = O.detector_labels(kmap, valid, include_mask=True, noise=torch.from_numpy(g["lab_noise"]))
     assert np.array_equal(labels.numpy(), g["lab_labels"]) and np.array_equal(cells.numpy(), g["lab_cells"])
+
+
+def test_eval_oracle_matches_reference(golden):
+    """oracle/eval_oracle.py (repeatability, keep_shared_points, cross-checked matching) against the values the unmodified
+    reference produced on the same synthetic pairs: rationals and point lists bit-equal, cv2 distances within 1e-6."""
+    from conftest import make_eval_pair
+    from oracle import eval_oracle as E
+    g = golden("eval_cases.npz")
+    reps = []
+    for k, seed in enumerate(g["seeds"]):
+        d = make_eval_pair(int(seed))
+        for kk, thr in ((300, 3), (50, 1)):
+            rep = E.repeatability_pair(d["prob"], d["warped_prob"], d["homography"], kk, thr)[0]
+            assert rep == float(g[f"rep{k}_k{kk}_t{thr}"]), (k, kk, thr)
+        reps.append(E.repeatability_pair(d["prob"], d["warped_prob"], d["homography"], 300, 3)[0])
+        for kk in (1000, 60):
+            kp1 = E.keep_shared_points(d["prob"], d["homography"], kk)
+            kp2 = E.keep_shared_points(d["warped_prob"], np.linalg.inv(d["homography"]), kk)
+            assert np.array_equal(kp1, g[f"hom{k}_k{kk}_kp1"]) and np.array_equal(kp2, g[f"hom{k}_k{kk}_kp2"])
+            pairs, dist = E.order_matches(*E.mutual_nn(d["desc"][kp1[:, 0], kp1[:, 1]], d["warped_desc"][kp2[:, 0], kp2[:, 1]]))
+            assert np.array_equal(pairs, g[f"hom{k}_k{kk}_matches"]), (k, kk)
+            assert np.abs(dist - g[f"hom{k}_k{kk}_dist"]).max() < 1e-6
+            assert len(pairs) / len(kp1) == float(g[f"hom{k}_k{kk}_score"])
+    assert abs(np.mean(reps) - float(g["rep_all_k300_t3"])) < 1e-12
+    # degenerate inputs the reference handles: no detections on one / both sides
+    z = np.zeros((32, 40), np.float32)
+    one = z.copy()
+    one[5, 7] = 0.5
+    assert np.isnan(E.repeatability_pair(z, z, np.eye(3))[0])
+    assert E.repeatability_pair(one, z, np.eye(3))[:3] == (0.0, 1, 0)
+    assert E.repeatability_pair(one, one, np.eye(3)) == (1.0, 1, 1, 1, 1)
+    assert E.mutual_nn(np.zeros((0, 256), np.float32), np.ones((3, 256), np.float32))[0].shape == (0, 2)
+
+
+def test_nerf_step_oracle_matches_reference(golden):
+    """oracle/eval_oracle.nerf_step (NMS -> nonzero -> depth-aware re-projection -> border filter -> ordered 3x3 splat)
+    against ExportNeRFDetections.step of the unmodified reference run with a stub model: bit-equal maps."""
+    from conftest import make_nerf_batch
+    from oracle import eval_oracle as E
+    g = golden("nerf_step.npz")
+    for c in range(int(g["n"])):
+        bseed, nv, j, k = (int(v) for v in g[f"case{c}"])
+        bt = make_nerf_batch(bseed, n_views=nv)
+        raw = bt["raw"]
+        got, pts = E.nerf_step(torch.from_numpy(g[f"heat{c}"]), raw["input_depth"][k], bt["camera_intrinsic_matrix"][j],
+                               raw["input_rotation"][k], raw["input_translation"][k], raw["input_rotation"][j],
+                               raw["input_translation"][j], int(g["nms"]), float(g["det_thresh"]), int(g["top_k"]), O.box_nms)
+        assert len(pts) > 50
+        assert np.array_equal(got, g[f"splat{c}"]), f"case {c}"
