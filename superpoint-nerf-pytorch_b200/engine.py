@@ -139,7 +139,7 @@ def main(config_path: str,
         config_path: Path to configuration.
         task: The task to be performed.
         synthetic: feed this many synthetic images instead of the dataset loader.
-        random_init: skip loading `pretrained` (benchmarking with random-init weights).
+        random_init: skip loading `pretrained` (benchmarking with random-init weights, torch.manual_seed(0) on every rank).
     """
     if task in ("train", "export_NeRF_labels"):   # ExportNeRFDetections is available as a class (engine_solvers/export.py); the NeRF
         # dataset loader that feeds it is not part of this package
@@ -149,6 +149,8 @@ def main(config_path: str,
     if not torch.cuda.is_available():
         raise SystemExit("CUDA is not available: this implementation has no CPU fallback")
     rank, world, device = init_distributed()
+    if random_init:
+        torch.manual_seed(0)      # every rank (and every run) gets the same random-init weights
     model = get_model(config["model"], device=device)
     if not random_init:
         assert config["pretrained"], "Use pretrained model to export."
