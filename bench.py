@@ -18,7 +18,9 @@ CUDA events inside the library during the timed region; `kernels` lists the same
 25 of 100 homographies); `gpu_reference` = the same port with device="cuda" (stock cuDNN with torch's TF32 default,
 torchvision's CUDA nms, 100 sequential batch-1 steps) - the honest GPU bar next to the CPU figure.
 
-`--impl reference` times the reference's CPU path (oracle port, the reference is pure Python) on the host cores.
+`--impl reference` times the reference's CPU path (oracle port, the reference is pure Python) on the host cores: exactly
+--steps timed steps after --warmup untimed ones, each a bounded sample (1 image x h of the 100 homographies, h sized so
+the run takes about --ref-budget-s seconds), same `config` object as the native arm.
 """
 from __future__ import annotations
 
@@ -36,6 +38,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 H, W, NUM_H = 240, 320, 100
+WORKLOAD = "MagicPoint HA pseudo-label export, 240x320, 100 homographies (configs[1])"
 MODEL_CFG = {"script": "SuperPoint", "class_name": "SuperPoint", "model_name": "magicpoint",
              "vgg_cn": [64, 64, 64, 64, 128, 128, 128, 128],
              "detector_head": {"detector_dim": [128, 256], "grid_size": 8, "nms": 4, "det_thresh": 0.015, "top_k": 0}}
@@ -117,6 +120,23 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def workload_config(args, world):
+    """`config` of BOTH arms' JSON lines - the reference arm runs on the native arm's config, so the two lines carry the
+    identical object: the workload, how the native arm runs it, and (labelled) how the reference arm samples it."""
+    ips = args.images_per_step
+    return {"workload": WORKLOAD, "images_per_step_per_gpu": ips, "forwards_per_step_per_gpu": ips * NUM_H,
+            "precision": args.precision, "weights": "random-init", "sampler": "device", "streams": args.streams,
+            "parallelism": f"image-sharded x{world}",
+            "kernel_timing": "per-kernel durations (roofline, kernels[]) come from a second pass over the same K steps "
+                             "with a CUDA event pair around every launch; value/ms_per_step are the uninstrumented pass",
+            "l2_policy": "no explicit flush: each step streams > 1 GB of fresh activations per GPU (>> 126 MB L2) "
+                         "and uses images not seen before",
+            "reference_arm": "bench.py --impl reference runs the same workload through the CPU oracle port of the reference "
+                             "(torch-CPU fp32, all host threads, incl. the in-model NMS the reference pays for): every step is a "
+                             "bounded sample, 1 image x h of the 100 homographies, extrapolated linearly; images_per_step / "
+                             "precision / sampler / streams describe the native arm"}
+
+
 def random_init_state_dict():
     """torch default init under torch.manual_seed(0) of the reference architecture (parameter holder only)."""
     import torch
@@ -164,21 +184,32 @@ def cpu_reference_sample(n_hom: int, threads: int | None = None, device: str | N
 
 
 def run_reference(args):
+    """The reference arm: exactly `--steps` timed steps after `--warmup` untimed ones, each step one bounded sample of
+    the workload (1 image x h of the 100 homographies through the CPU oracle port, all host threads).  h is fixed for
+    the run, chosen from a two-homography calibration so that warm-up + timed steps take about `--ref-budget-s` seconds
+    (2 <= h <= --ref-homographies).  value = images' worth of work done in the timed steps / their wall time."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    vals = []
-    for i in range(args.warmup_ref + args.steps_ref):
-        r = cpu_reference_sample(args.ref_homographies)
-        if i >= args.warmup_ref:
-            vals.append(r)
-    v = sum(x["img_per_s"] for x in vals) / len(vals)
-    ms = 1e3 * sum(x["seconds"] for x in vals) / len(vals)
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    calib = cpu_reference_sample(2)
+    per_h = calib["seconds"] / 2
+    h = int(min(max(2, args.ref_budget_s / ((steps + warmup) * per_h)), max(2, args.ref_homographies)))
+    timed = []
+    for i in range(warmup + steps):
+        r = cpu_reference_sample(h)
+        if i >= warmup:
+            timed.append(r["seconds"])
+    total = sum(timed)
+    v = steps * (h / NUM_H) / total
+    sample = (f"{steps} timed steps (+{warmup} warm-up), each 1 image x {h} of {NUM_H} homographies (240x320, full model forward "
+              f"incl. in-model NMS, kornia-shim warps) on host cores, linearly extrapolated to {NUM_H}")
     line = {"impl": "reference", "metric": "pseudo-label img/s (240x320, 100 H)", "value": v, "unit": "img/s",
-            "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": ms,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * total / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MagicPoint HA export 240x320, 100 homographies (configs[1]); CPU oracle port of the reference"},
-            "cpu_baseline": {"value": v, "unit": "img/s", "cores": vals[0]["cores"], "kind": "port", "sample": vals[0]["sample"]},
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": calib["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -369,13 +400,7 @@ def run_native(args):
             "ms_per_step_instrumented": ms_instr / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "f16": "f16", "bf16": "bf16", "f16x3": "f16x3 (fp16 hi/lo split, fp32-grade)"}[args.precision], "data": "synthetic",
-            "config": {"workload": "MagicPoint HA pseudo-label export, 240x320, 100 homographies (configs[1])",
-                       "images_per_step_per_gpu": ips, "forwards_per_step_per_gpu": ips * NUM_H, "precision": args.precision,
-                       "weights": "random-init", "sampler": "device", "streams": args.streams, "parallelism": f"image-sharded x{world}",
-                       "kernel_timing": "per-kernel durations (roofline, kernels[]) come from a second pass over the same K steps "
-                                        "with a CUDA event pair around every launch; value/ms_per_step are the uninstrumented pass",
-                       "l2_policy": "no explicit flush: each step streams > 1 GB of fresh activations per GPU (>> 126 MB L2) "
-                                    "and uses images not seen before"},
+            "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": ips * H * W * 4,
                     "d2h_bytes_per_step": ips * (max_kp * 2 * 4 + 4), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
@@ -411,14 +436,11 @@ def main():
     ap.add_argument("--max-forwards", type=int, default=400)
     ap.add_argument("--streams", type=int, default=1)
     ap.add_argument("--ref-homographies", type=int, default=25, help="homographies in the bounded CPU sample (of 100)")
-    ap.add_argument("--steps-ref", type=int, default=1)
-    ap.add_argument("--warmup-ref", type=int, default=0)
+    ap.add_argument("--ref-budget-s", type=float, default=150.0,
+                    help="--impl reference: target wall time of warm-up + timed steps; sets the homographies per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        # bounded: the driver passes its own --steps/--warmup; each reference step is one bounded sample
-        args.steps_ref = max(1, min(args.steps, 2))
-        args.warmup_ref = 0
         run_reference(args)
     else:
         run_native(args)

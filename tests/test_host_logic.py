@@ -295,3 +295,32 @@ def test_nerf_point_reprojection_mirror_matches_the_oracle(golden):
         kept, mask = filter_points(got, (h, w), return_mask=True)
         ok = (want[:, 0] >= 0) & (want[:, 0] < h - 1) & (want[:, 1] >= 0) & (want[:, 1] < w - 1)
         assert torch.equal(mask, ok) and torch.equal(kept, want[ok]) and 0 < int(ok.sum()) < len(pts)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU): one JSON line with the native arm's metric / unit / config, exactly the
+    requested steps and warm-up, cpu_baseline describing the run and an e2e object with zero copies; ranks other than 0
+    print nothing."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import types
+    from conftest import ROOT
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1", "--ref-budget-s", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, WORLD_SIZE="2", RANK="0"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "pseudo-label img/s (240x320, 100 H)" and d["unit"] == "img/s"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 2 and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "2 timed steps (+1 warm-up)" in d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    sys.path.insert(0, str(ROOT))
+    import bench
+    args = types.SimpleNamespace(images_per_step=128, precision="f16", streams=1)
+    assert d["config"] == bench.workload_config(args, 2)          # the same object the native arm prints
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, WORLD_SIZE="2", RANK="1"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
