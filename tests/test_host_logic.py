@@ -324,3 +324,33 @@ def test_bench_reference_arm_contract():
     assert d["config"] == bench.workload_config(args, 2)          # the same object the native arm prints
     other = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(os.environ, WORLD_SIZE="2", RANK="1"))
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_cabi_rejects_null_context_without_a_gpu(built_lib):
+    """Error behaviour at the boundary (include/spn_b200.h: 'return 0 or a negative SPN_E_* code with spn_last_error()'):
+    every entry point called with a NULL context and zeroed arguments returns a negative code and sets a message - no
+    crash, no CUDA call needed.  Runs in a child process so that a null dereference could not take pytest down."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import sys, ctypes as C
+sys.path.insert(0, %r)
+from superpoint_nerf_pytorch_b200 import _native as N
+lib = N.load_library()
+skip = {"spn_last_error", "spn_version", "spn_create", "spn_destroy", "spn_launch_count"}
+n = 0
+for name, (res, args) in N.PROTOTYPES.items():
+    if name in skip:
+        continue
+    vals = [None if (a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents")) else a(0) for a in args]
+    rc = getattr(lib, name)(*vals)
+    msg = lib.spn_last_error().decode()
+    assert rc < 0 and msg, (name, rc, msg)
+    n += 1
+assert lib.spn_launch_count(None) == -1 and lib.spn_destroy(None) == 0 and lib.spn_version() >= 100
+print("checked", n)
+''' % str(ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "checked 26" in out.stdout, out.stdout
