@@ -383,3 +383,24 @@ def test_split_mode_ha_export_vs_golden_and_oracle(golden):
     a, b = keypoint_agreement(eng.keypoints(heat)[0], want["keypoints"])
     print(f"f16x3 HA random-init 240x320: heatmap rel err {err:.2e}, keypoints {a:.4f}/{b:.4f}")
     assert err < STRICT and a >= 0.99 and b >= 0.99
+
+
+@pytest.mark.parametrize("precision,gate", [("f16", FAST), ("f16x3", 1e-4)])
+def test_forward_full_hd_vs_oracle(precision, gate):
+    """Largest size exercised: one 1080x1920 frame (27x the pixels of the export config; 135 x 240 cells, 32 400 front-end
+    tiles, workspace regrown) through both tensor-core modes against the CPU oracle, in-model NMS off."""
+    from superpoint_nerf_pytorch_b200.utils.get_model import get_model
+    H, W = 1080, 1920
+    sd = O.make_state_dict("magicpoint", seed=12, logit_gain=5.0)
+    c = copy.deepcopy(MP_MODEL)
+    c["detector_head"]["nms"] = 0
+    m = get_model(dict(c, precision=precision), "cuda").eval()
+    m.load_state_dict(sd)
+    x = torch.from_numpy(smooth_image(H, W, 321))[None, None]
+    want = O.model_forward(sd, x, c)["detector_output"]
+    got = m(x.cuda())["detector_output"]
+    e1 = rel_err(got["logits"].cpu().numpy(), want["logits"].numpy())
+    e2 = rel_err(got["prob_heatmap"].cpu().numpy(), want["prob_heatmap"].numpy())
+    print(f"1080x1920 [{precision}]: logits {e1:.2e} prob {e2:.2e}")
+    assert e1 < gate and e2 < gate, (e1, e2)
+    assert torch.equal(got["pred_pts"], (got["prob_heatmap"] >= c["detector_head"]["det_thresh"]).to(torch.int32))
