@@ -427,6 +427,42 @@ def main():
     np.savez_compressed(OUT / "nerf_step.npz", **ns)
     print("nerf step splats", [int((ns[f"splat{c}"] > 0).sum()) for c in range(3)])
 
+    # ---- 12. ExportDetections variants the GPU tests check against the oracle: aggregation 'max' (export.py:107-110)
+    #          and enable_HA False (export.py:93-95: one plain forward, then the same NMS / threshold / nonzero) -----------
+    hv = {}
+    sdv = O.make_state_dict("magicpoint", seed=11, logit_gain=12.0)
+    modelv = SuperPoint(copy.deepcopy(MP_MODEL)).eval()
+    modelv.load_state_dict(sdv)
+    imgv = torch.from_numpy(smooth_image(120, 160, 34))[None, None]
+    orig_nms_v = refexport.box_nms
+    orig_sample_v = Homographic_aug.sample_homography
+    for tag, agg_mode, enable in (("max", "max", True), ("noha", "sum", False)):
+        cap, used = {}, []
+
+        def spy_nms_v(prob, _c=cap, **kw):
+            _c["agg"] = prob.clone()
+            return orig_nms_v(prob=prob, **kw)
+
+        def spy_sample_v(self, *a, _u=used, **kw):
+            h = orig_sample_v(self, *a, **kw)
+            _u.append(h.clone())
+            return h
+
+        refexport.box_nms = spy_nms_v
+        Homographic_aug.sample_homography = spy_sample_v
+        cfgv = {"data": {"experiment_name": f"golden_{tag}"}, "homography_adaptation": dict(HA_CFG, aggregation=agg_mode),
+                "model": copy.deepcopy(MP_MODEL)}
+        np.random.seed(321)
+        refexport.ExportDetections(cfgv, modelv, [{"raw": {"image": imgv}, "name": ["img0"]}], "training", enable, "cpu")
+        refexport.box_nms = orig_nms_v
+        Homographic_aug.sample_homography = orig_sample_v
+        hv[f"{tag}_agg"] = cap["agg"].numpy()
+        hv[f"{tag}_keypoints"] = np.load(Path(exper, "outputs", f"golden_{tag}", "training", "img0.npy"))
+        hv[f"{tag}_H"] = torch.cat(used).numpy() if used else np.zeros((0, 3, 3), np.float32)
+    hv.update(image=imgv.numpy(), seed=np.array(11), gain=np.array(12.0), np_seed=np.array(321))
+    np.savez_compressed(OUT / "ha_export_variants.npz", **hv)
+    print("ha_export variants", {k: v.shape for k, v in hv.items() if k.endswith("keypoints") or k.endswith("_H")})
+
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

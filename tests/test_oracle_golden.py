@@ -194,3 +194,24 @@ def test_nerf_step_oracle_matches_reference(golden):
                                raw["input_translation"][j], int(g["nms"]), float(g["det_thresh"]), int(g["top_k"]), O.box_nms)
         assert len(pts) > 50
         assert np.array_equal(got, g[f"splat{c}"]), f"case {c}"
+
+
+def test_ha_export_variants_match_reference(golden):
+    """The two ExportDetections variants the GPU tests check against the oracle - aggregation 'max' (export.py:107-110)
+    and enable_HA False (one plain forward, export.py:93-95) - pinned to the unmodified reference: aggregated map (the
+    input of the final box_nms) and keypoint file bit-equal."""
+    g = golden("ha_export_variants.npz")
+    sd = O.make_state_dict("magicpoint", seed=int(g["seed"]), logit_gain=float(g["gain"]))
+    img = torch.from_numpy(g["image"])
+    r = O.homography_adaptation(sd, img, {"homography_adaptation": dict(HA_CFG, aggregation="max"), "model": MP_MODEL},
+                                homographies=torch.from_numpy(g["max_H"]))
+    assert np.array_equal(r["mean_prob"].numpy(), g["max_agg"][0] if g["max_agg"].ndim == 3 else g["max_agg"])
+    assert np.array_equal(r["keypoints"], g["max_keypoints"])
+    np.random.seed(int(g["np_seed"]))           # the same homographies from numpy's global RNG in the reference's order
+    r2 = O.homography_adaptation(sd, img, {"homography_adaptation": dict(HA_CFG, aggregation="max"), "model": MP_MODEL})
+    assert np.array_equal(r2["homographies"].numpy(), g["max_H"]) and np.array_equal(r2["keypoints"], g["max_keypoints"])
+    r3 = O.homography_adaptation(sd, img, {"homography_adaptation": dict(HA_CFG, num=1), "model": MP_MODEL})
+    assert g["noha_H"].shape[0] == 0
+    assert np.array_equal(r3["mean_prob"].numpy(), g["noha_agg"][0] if g["noha_agg"].ndim == 3 else g["noha_agg"])
+    assert np.array_equal(r3["keypoints"], g["noha_keypoints"])
+    assert len(g["max_keypoints"]) != len(g["noha_keypoints"])
