@@ -215,3 +215,33 @@ def test_ha_export_variants_match_reference(golden):
     assert np.array_equal(r3["mean_prob"].numpy(), g["noha_agg"][0] if g["noha_agg"].ndim == 3 else g["noha_agg"])
     assert np.array_equal(r3["keypoints"], g["noha_keypoints"])
     assert len(g["max_keypoints"]) != len(g["noha_keypoints"])
+
+
+def test_ha_masks_oracle_matches_reference(golden):
+    """O.ha_masks (nearest warps of ones by H and H^-1 + elliptical erosion, export.py:49-66) against the 46 masks and 46
+    counts ExportDetections.step of the unmodified reference produced at five image sizes and four margins."""
+    g = golden("ha_masks.npz")
+    total = 0
+    for ci in range(int(g["n"])):
+        h, w, margin, n = (int(v) for v in g[f"c{ci}_par"])
+        want_m = np.unpackbits(g[f"c{ci}_mask"], axis=-1)[..., :w]
+        want_c = np.unpackbits(g[f"c{ci}_count"], axis=-1)[..., :w]
+        Hs = torch.from_numpy(g[f"c{ci}_H"])
+        for i in range(n):
+            m, c, _ = O.ha_masks(Hs[i:i + 1], (h, w), margin)
+            assert np.array_equal(m[0].numpy(), want_m[i]) and np.array_equal(c[0].numpy(), want_c[i]), (ci, i)
+            total += 1
+    assert total == 46
+
+
+def test_hpatches_export_values_match_reference(golden):
+    """The oracle forward on the HPatches-style pair = the values Export_Hpatches_Repeatability / _Descriptors of the
+    unmodified reference wrote (prob_heatmap_nms of both images, (H,W,256) descriptors at sampled points)."""
+    g = golden("hpatches_export.npz")
+    sd = O.make_state_dict("superpoint", seed=4, logit_gain=12.0)
+    pts = g["des_pts"]
+    for img_key, prob_key, desc_key in (("image", "rep_prob", "des_desc_at_pts"), ("warped_image", "rep_warped_prob", "des_warped_desc_at_pts")):
+        out = O.model_forward(sd, torch.from_numpy(g[img_key]), SP_MODEL)
+        assert np.array_equal(out["detector_output"]["prob_heatmap_nms"][0].numpy(), g[prob_key])
+        desc = out["descriptor_output"]["desc"][0].numpy().transpose(1, 2, 0)
+        assert np.array_equal(desc[pts[:, 0], pts[:, 1]], g[desc_key])
