@@ -354,3 +354,16 @@ print("checked", n)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "checked 26" in out.stdout, out.stdout
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a machine without a GPU")
+def test_bench_native_arm_fails_loudly_without_a_gpu():
+    """`python bench.py` (native arm) must not produce a number on a machine without a GPU: non-zero exit, no JSON line
+    (a silent CPU or library fallback would print one)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu-baseline"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode != 0
+    assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
